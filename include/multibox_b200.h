@@ -1,0 +1,157 @@
+/* multibox_b200 -- C ABI of the B200-native Multibox hot path.
+ *
+ * Drop-in boundary for the data-parallel hot path of gvanhorn38/multibox:
+ *   - GT -> prior bipartite matching      (reference loss.py:8-53, the body of
+ *                                          the tf.py_func at loss.py:81-82)
+ *   - multibox loss forward + backward    (reference loss.py:55-117 + TF autodiff)
+ *   - detection post-processing           (reference detect.py:74-131, 408-443;
+ *                                          eval.py:142-175)
+ *
+ * Conventions (all functions):
+ *   - every pointer is a DEVICE pointer into memory owned by the caller
+ *     (PyTorch); the library allocates nothing persistent and keeps no global
+ *     state besides the thread-local error string;
+ *   - tensors are dense, row-major, float32 / int32 unless said otherwise and
+ *     16-byte aligned;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises the device;
+ *   - the return value is 0 on success, a negative MBX_E_* code for argument
+ *     errors, or a positive cudaError_t; mbx_last_error() describes it;
+ *   - data-dependent failures (NaN / -inf cost entries, infeasible matrices:
+ *     the cases where scipy.optimize.linear_sum_assignment raises ValueError at
+ *     reference loss.py:40) are reported asynchronously in a device status
+ *     word (MBX_STATUS_* bits) that the host mirror reads back and turns into
+ *     the same ValueError;
+ *   - functions are re-entrant across streams as long as each in-flight call
+ *     has its own workspace.
+ */
+#ifndef MULTIBOX_B200_H
+#define MULTIBOX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBX_VERSION 100
+
+/* argument errors (negative return values) */
+#define MBX_E_ARG        (-1)   /* null / misaligned pointer, bad size          */
+#define MBX_E_TOO_LARGE  (-2)   /* P or M beyond what one CTA's shared memory holds */
+#define MBX_E_WORKSPACE  (-3)   /* workspace too small                          */
+
+/* device status word bits */
+#define MBX_STATUS_INVALID_COST  1u  /* NaN or -inf cost entry (scipy: "matrix contains invalid numeric entries") */
+#define MBX_STATUS_INFEASIBLE    2u  /* no finite assignment (scipy: "cost matrix is infeasible") */
+#define MBX_STATUS_BAD_NUM_GT    4u  /* num_gt[b] outside [0, M] (clamped)      */
+
+/* flags */
+#define MBX_FLAG_LOGITS        1u   /* `confidences` holds logits; the kernel applies the
+                                       sigmoid of reference model.py:322 and the confidence
+                                       gradient is returned w.r.t. the logits */
+#define MBX_FLAG_BOUNDARY      2u   /* strict py_func boundary (reference loss.py:81): locations
+                                       already have the prior added, confidences already have
+                                       +1e-10 added; `priors` is ignored */
+#define MBX_FLAG_WARPS_SHIFT   8    /* bits 8..15: force CTA size in warps (0 = heuristic) */
+
+int         mbx_version(void);
+const char *mbx_last_error(void);
+
+/* Number of SMs / max dynamic shared memory the library sees on the current device. */
+int mbx_device_info(int *sm_count, int *max_smem_per_block);
+
+/* ------------------------------------------------------------------------- *
+ * Matching (+ fused loss forward/backward)
+ * ------------------------------------------------------------------------- */
+
+/* Bytes of scratch mbx_match_loss needs for a batch of B images.  The first
+ * use of a workspace must see it zero-filled; the library leaves it reusable. */
+size_t mbx_match_workspace_bytes(int B, int P, int M);
+
+/* One pass of the training hot path over a batch.
+ *
+ * Replaces: reference loss.py:8-53 (compute_assignments: log terms, cost
+ * matrix, scipy linear_sum_assignment, mask + stacked GT) and, when the loss
+ * outputs are requested, loss.py:67-74,88-101 plus the gradients TF autodiff
+ * derives from them (and model.py:322 with MBX_FLAG_LOGITS).
+ *
+ * Inputs
+ *   locations    [B,P,4]  predicted offsets (or absolute boxes with MBX_FLAG_BOUNDARY)
+ *   confidences  [B,P]    post-sigmoid confidences (logits with MBX_FLAG_LOGITS)
+ *   gt_bboxes    [B,M,4]  zero-padded ground truth (reference inputs.py:346-348)
+ *   num_gt       [B]      int32, real GT count per image, 0 <= n <= M <= P
+ *   priors       [P,4]    prior boxes (NULL with MBX_FLAG_BOUNDARY)
+ *   alpha                 LOCATION_LOSS_ALPHA
+ * Outputs (each may be NULL = not wanted)
+ *   mask            [B,P]   int32 0/1            (reference: assignment_partitions)
+ *   matched_gt_idx  [B,P]   int32 GT index or -1
+ *   stacked_gt      [cap,4] matched GT rows in (image, ascending prior) order
+ *                           (reference: stacked_gt_bboxes); cap >= sum(num_gt)
+ *   d_locations     [B,P,4] dL/d locations
+ *   d_confidences   [B,P]   dL/d confidences (d logits with MBX_FLAG_LOGITS)
+ *   confidences_out [B,P]   sigmoid(logits) (MBX_FLAG_LOGITS only)
+ *   results         [8]     float32: [0] location_loss, [1] confidence_loss,
+ *                           [2] status word (exact small integer), [3] number of
+ *                           matched priors (exact while < 2^24), [4..7] the two
+ *                           losses as float64 (2 x 8 bytes)
+ *   n_stacked       [1]     int32 number of rows written to stacked_gt
+ * The status word is also OR-ed into results[2]; it is 0 when every image was
+ * solved.  grads/loss outputs are produced iff `results` is non-NULL.
+ */
+int mbx_match_loss(const float *locations, const float *confidences,
+                   const float *gt_bboxes, const int32_t *num_gt,
+                   const float *priors, int B, int P, int M, float alpha,
+                   unsigned flags,
+                   int32_t *mask, int32_t *matched_gt_idx,
+                   float *stacked_gt, int32_t *n_stacked,
+                   float *d_locations, float *d_confidences,
+                   float *confidences_out, float *results,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Detection post-processing
+ * ------------------------------------------------------------------------- */
+
+size_t mbx_detect_workspace_bytes(int B, int P, int k_max);
+
+/* One pass of detection post-processing over a batch of patches.
+ *
+ * Replaces the per-image loop body of reference detect.py:408-436: decode
+ * (:412), clip (:413), filter_proposals (:74-104), descending confidence sort
+ * and top max_to_keep (:423-427; ties broken as numpy's stable argsort followed
+ * by reversal does: equal confidences in DESCENDING prior index), optional
+ * greedy NMS on the kept boxes (extension: no reference counterpart), and
+ * convert_proposals (:106-131, float64).  With restrictions [0,0,1,1] and
+ * nms_iou < 0 it is also the decode/sort/top-k of reference eval.py:146-167.
+ *
+ * Inputs
+ *   locations    [B,P,4], confidences [B,P] (logits with MBX_FLAG_LOGITS), priors [P,4]
+ *   restrictions [B,4]   float32 x1,y1,x2,y2 limits (NULL = [0,0,1,1] everywhere)
+ *   max_to_keep  [B]     int32 (NULL = k_max everywhere); clamped to k_max
+ *   offsets      [B,2]   int32 (y,x) patch offset    } NULL = identity conversion
+ *   patch_dims   [B,2]   int32 (h,w)                 }
+ *   image_dims   [B,2]   int32 (h,w)                 }
+ *   is_flipped   [B]     int32                       }
+ *   nms_iou              IoU threshold; < 0 disables NMS
+ * Outputs (padded to k_max per image; rows >= count are zero / -1)
+ *   out_boxes    [B,k_max,4] float64 image coordinates (NULL = not wanted)
+ *   out_patch_boxes [B,k_max,4] float32 decoded+clipped patch coordinates (NULL ok)
+ *   out_scores   [B,k_max]   float32
+ *   out_prior_idx[B,k_max]   int32 original prior index
+ *   out_count    [B]         int32 detections kept
+ */
+int mbx_detect(const float *locations, const float *confidences, const float *priors,
+               const float *restrictions, const int32_t *max_to_keep,
+               const int32_t *offsets, const int32_t *patch_dims,
+               const int32_t *image_dims, const int32_t *is_flipped,
+               int B, int P, int k_max, float nms_iou, unsigned flags,
+               double *out_boxes, float *out_patch_boxes, float *out_scores,
+               int32_t *out_prior_idx, int32_t *out_count,
+               void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MULTIBOX_B200_H */

@@ -1,0 +1,428 @@
+// multibox_b200 -- detection post-processing, one CTA per image / patch
+// (persistent grid), sm_100a.
+//
+// What it replaces (reference = gvanhorn38/multibox):
+//   detect.py:412-413  decode (offset + prior) and clip to [0,1]       -> load phase
+//   detect.py:74-104   filter_proposals (per-box python loop)          -> load phase (predicate)
+//   detect.py:423-427  argsort(conf)[::-1][:max_to_keep]               -> 64-bit key sort in shared
+//                      memory; key = (orderable(conf) << 32 | prior index), descending, which is the
+//                      order numpy's stable argsort + reversal yields (ties: descending index)
+//   (extension)        greedy NMS on the kept boxes, bitmask formulation: one warp ballot per
+//                      (row, 32-column word) builds the suppression matrix in shared memory, one
+//                      warp sweeps it in score order
+//   detect.py:106-131  convert_proposals (float64 scale/offset/flip)   -> store phase
+//   model.py:322       sigmoid (MBX_FLAG_LOGITS)                       -> load phase
+//   eval.py:146-167    decode / clip / full sort / top-100             -> same kernel, no filter
+#include <math_constants.h>
+
+#include "mbx_common.cuh"
+
+namespace mbx {
+
+struct DetectParams {
+    const float *locations, *confidences, *priors, *restrictions;
+    const int32_t *max_to_keep, *offsets, *patch_dims, *image_dims, *is_flipped;
+    int B, P, k_max, n2;
+    float nms_iou;
+    unsigned flags;
+    double *out_boxes;
+    float *out_patch_boxes, *out_scores;
+    int32_t *out_idx, *out_count;
+};
+
+// monotone float32 -> uint32 map (larger float => larger uint)
+__device__ __forceinline__ uint32_t orderable(float f) {
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+__device__ __forceinline__ float clip01(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); }
+
+// fp32 IoU exactly as oracle/np_oracle.greedy_nms (and torchvision's CPU nms) computes it
+__device__ __forceinline__ bool iou_gt(float4 a, float area_a, float4 b, float area_b, float thr) {
+    float w = fmaxf(0.0f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+    float h = fmaxf(0.0f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+    float inter = __fmul_rn(w, h);
+    float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+    return iou > thr;
+}
+
+struct DSmem {
+    float4 *priors, *box, *sbox;
+    unsigned long long *keys;
+    float *sarea;
+    uint32_t *nmask, *keepw;
+    int *keeppre, *cnt;
+    uint64_t *bar;
+};
+
+__host__ __device__ inline size_t dalign(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline size_t dcarve(DSmem *s, unsigned char *base, int P, int n2, int k_max, bool nms) {
+    const int W = (k_max + 31) / 32;
+    size_t o = 0;
+    auto take = [&](size_t bytes, size_t al) {
+        o = dalign(o, al);
+        size_t r = o;
+        o += bytes;
+        return r;
+    };
+    size_t o_pri = take(sizeof(float4) * P, 16);
+    size_t o_box = take(sizeof(float4) * P, 16);
+    size_t o_sbox = take(nms ? sizeof(float4) * k_max : 0, 16);
+    size_t o_keys = take(sizeof(unsigned long long) * n2, 8);
+    size_t o_bar = take(8, 8);
+    size_t o_area = take(nms ? sizeof(float) * k_max : 0, 4);
+    size_t o_nm = take(nms ? sizeof(uint32_t) * static_cast<size_t>(k_max) * W : 0, 4);
+    size_t o_kw = take(sizeof(uint32_t) * 32, 4);
+    size_t o_kp = take(sizeof(int) * 33, 4);
+    size_t o_cnt = take(sizeof(int) * 2, 4);
+    if (s) {
+        s->priors = reinterpret_cast<float4 *>(base + o_pri);
+        s->box = reinterpret_cast<float4 *>(base + o_box);
+        s->sbox = reinterpret_cast<float4 *>(base + o_sbox);
+        s->keys = reinterpret_cast<unsigned long long *>(base + o_keys);
+        s->bar = reinterpret_cast<uint64_t *>(base + o_bar);
+        s->sarea = reinterpret_cast<float *>(base + o_area);
+        s->nmask = reinterpret_cast<uint32_t *>(base + o_nm);
+        s->keepw = reinterpret_cast<uint32_t *>(base + o_kw);
+        s->keeppre = reinterpret_cast<int *>(base + o_kp);
+        s->cnt = reinterpret_cast<int *>(base + o_cnt);
+    }
+    return dalign(o, 16);
+}
+
+template <int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectParams p) {
+    constexpr int T = NWARPS * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DSmem s;
+    const bool nms = p.nms_iou >= 0.0f;
+    dcarve(&s, smem_raw, p.P, p.n2, p.k_max, nms);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = p.P, N2 = p.n2, KM = p.k_max;
+    const bool logits = (p.flags & MBX_FLAG_LOGITS) != 0;
+
+    if (tid == 0) {
+        mbar_init(s.bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(s.bar, static_cast<uint32_t>(sizeof(float4) * P));
+        bulk_copy_g2s(s.priors, p.priors, static_cast<uint32_t>(sizeof(float4) * P), s.bar);
+    }
+    bool priors_ready = false;
+
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+        if (!priors_ready) {
+            mbar_wait(s.bar, 0);
+            priors_ready = true;
+        }
+        const size_t row0 = static_cast<size_t>(b) * P;
+        float4 r = make_float4(0.f, 0.f, 1.f, 1.f);
+        if (p.restrictions) r = reinterpret_cast<const float4 *>(p.restrictions)[b];
+        if (tid == 0) s.cnt[0] = 0;
+        __syncthreads();
+        // ---- decode + clip + restriction filter + sort key
+        const float4 *gl = reinterpret_cast<const float4 *>(p.locations) + row0;
+        int mine = 0;
+        for (int j = tid; j < N2; j += T) {
+            unsigned long long key = 0ull;
+            if (j < P) {
+                float4 l = ld_stream_f4(gl + j);
+                const float4 q = s.priors[j];
+                l.x = clip01(__fadd_rn(l.x, q.x));
+                l.y = clip01(__fadd_rn(l.y, q.y));
+                l.z = clip01(__fadd_rn(l.z, q.z));
+                l.w = clip01(__fadd_rn(l.w, q.w));
+                s.box[j] = l;
+                float c = ld_stream_f(p.confidences + row0 + j);
+                if (logits) c = sigmoidf_(c);
+                c = __fadd_rn(c, 0.0f);   // -0.0 -> +0.0 so equal values share one key
+                const bool drop = (l.x < r.x) || (l.y < r.y) || (l.z > r.z) || (l.w > r.w);   // detect.py:92-99
+                if (!drop) {
+                    key = (static_cast<unsigned long long>(orderable(c)) << 32) | static_cast<unsigned>(j);
+                    ++mine;
+                }
+            }
+            s.keys[j] = key;
+        }
+        if (mine) atomicAdd(&s.cnt[0], mine);
+        __syncthreads();
+        // ---- bitonic sort, descending
+        for (int k = 2; k <= N2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (N2 >> 1); t += T) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int ixj = i | j;
+                    const unsigned long long a = s.keys[i], c = s.keys[ixj];
+                    const bool desc = (i & k) == 0;
+                    if ((a < c) == desc) {
+                        s.keys[i] = c;
+                        s.keys[ixj] = a;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        int kk = s.cnt[0];
+        int keep = KM;
+        if (p.max_to_keep) {
+            keep = p.max_to_keep[b];
+            keep = keep < 0 ? 0 : (keep > KM ? KM : keep);
+        }
+        kk = kk < keep ? kk : keep;
+        int count = kk;
+        // ---- greedy NMS over the kk sorted survivors (extension)
+        if (nms) {
+            const int W = (kk + 31) >> 5;
+            for (int t = tid; t < kk; t += T) {
+                const float4 bx = s.box[static_cast<unsigned>(s.keys[t] & 0xffffffffu)];
+                s.sbox[t] = bx;
+                s.sarea[t] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+            }
+            __syncthreads();
+            // suppression matrix: bit j of nmask[i][w] <=> j = 32w+bit > i and IoU(i, j) > thr
+            const int WS = (KM + 31) >> 5;
+            for (int task = warp; task < kk * W; task += NWARPS) {
+                const int i = task / W, w = task - i * W;
+                if (w < (i >> 5)) continue;
+                const int jj = (w << 5) + lane;
+                bool sup = false;
+                if (jj > i && jj < kk) sup = iou_gt(s.sbox[i], s.sarea[i], s.sbox[jj], s.sarea[jj], p.nms_iou);
+                const unsigned bal = __ballot_sync(0xffffffffu, sup);
+                if (lane == 0) s.nmask[i * WS + w] = bal;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                unsigned rem = 0u, keptw = 0u;   // lane w owns bits [32w, 32w+32)
+                for (int i = 0; i < kk; ++i) {
+                    const int wd = i >> 5;
+                    const unsigned rw = __shfl_sync(0xffffffffu, rem, wd);
+                    if (!((rw >> (i & 31)) & 1u)) {
+                        if (lane == wd) keptw |= 1u << (i & 31);
+                        if (lane >= wd && lane < W) rem |= s.nmask[i * WS + lane];
+                    }
+                }
+                // exclusive prefix of kept counts per word
+                const int c = __popc(keptw);
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                s.keepw[lane] = keptw;
+                s.keeppre[lane] = inc - c;
+                if (lane == 31) s.keeppre[32] = inc;
+            }
+            __syncthreads();
+            count = s.keeppre[32];
+        }
+        // ---- store (convert_proposals in float64)
+        double sx = 1.0, sy = 1.0, ox = 0.0, oy = 0.0;
+        int flip = 0;
+        if (p.image_dims) {
+            const double ih = static_cast<double>(p.image_dims[2 * b]), iw = static_cast<double>(p.image_dims[2 * b + 1]);
+            sx = __ddiv_rn(static_cast<double>(p.patch_dims[2 * b + 1]), iw);
+            sy = __ddiv_rn(static_cast<double>(p.patch_dims[2 * b]), ih);
+            ox = __ddiv_rn(static_cast<double>(p.offsets[2 * b + 1]), iw);
+            oy = __ddiv_rn(static_cast<double>(p.offsets[2 * b]), ih);
+            flip = p.is_flipped ? p.is_flipped[b] : 0;
+        }
+        const size_t out0 = static_cast<size_t>(b) * KM;
+        if (!nms) {
+            for (int t = tid; t < KM; t += T) {
+                float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+                float sc = 0.f;
+                int idx = -1;
+                if (t < kk) {
+                    const unsigned long long key = s.keys[t];
+                    idx = static_cast<int>(key & 0xffffffffu);
+                    sc = from_orderable(static_cast<uint32_t>(key >> 32));
+                    bx = s.box[idx];
+                }
+                if (p.out_patch_boxes) reinterpret_cast<float4 *>(p.out_patch_boxes)[out0 + t] = bx;
+                if (p.out_scores) p.out_scores[out0 + t] = sc;
+                if (p.out_idx) p.out_idx[out0 + t] = idx;
+                if (p.out_boxes) {
+                    double x1 = 0., y1 = 0., x2 = 0., y2 = 0.;
+                    if (t < kk) {
+                        x1 = __dadd_rn(__dmul_rn(static_cast<double>(bx.x), sx), ox);
+                        y1 = __dadd_rn(__dmul_rn(static_cast<double>(bx.y), sy), oy);
+                        x2 = __dadd_rn(__dmul_rn(static_cast<double>(bx.z), sx), ox);
+                        y2 = __dadd_rn(__dmul_rn(static_cast<double>(bx.w), sy), oy);
+                        if (flip) {
+                            const double t1 = __dsub_rn(1.0, x2), t2 = __dsub_rn(1.0, x1);
+                            x1 = t1;
+                            x2 = t2;
+                        }
+                    }
+                    double2 *ob = reinterpret_cast<double2 *>(p.out_boxes) + 2 * (out0 + t);
+                    ob[0] = make_double2(x1, y1);
+                    ob[1] = make_double2(x2, y2);
+                }
+            }
+        } else {
+            // kept entries scatter to their rank; the tail [count, KM) is zero-filled
+            for (int t = tid; t < KM; t += T) {
+                const bool in_range = t < kk;
+                bool kept = false;
+                int pos = 0;
+                if (in_range) {
+                    const unsigned wbits = s.keepw[t >> 5];
+                    kept = (wbits >> (t & 31)) & 1u;
+                    pos = s.keeppre[t >> 5] + __popc(wbits & ((1u << (t & 31)) - 1u));
+                }
+                if (kept) {
+                    const unsigned long long key = s.keys[t];
+                    const int idx = static_cast<int>(key & 0xffffffffu);
+                    const float sc = from_orderable(static_cast<uint32_t>(key >> 32));
+                    const float4 bx = s.sbox[t];
+                    if (p.out_patch_boxes) reinterpret_cast<float4 *>(p.out_patch_boxes)[out0 + pos] = bx;
+                    if (p.out_scores) p.out_scores[out0 + pos] = sc;
+                    if (p.out_idx) p.out_idx[out0 + pos] = idx;
+                    if (p.out_boxes) {
+                        double x1 = __dadd_rn(__dmul_rn(static_cast<double>(bx.x), sx), ox);
+                        double y1 = __dadd_rn(__dmul_rn(static_cast<double>(bx.y), sy), oy);
+                        double x2 = __dadd_rn(__dmul_rn(static_cast<double>(bx.z), sx), ox);
+                        double y2 = __dadd_rn(__dmul_rn(static_cast<double>(bx.w), sy), oy);
+                        if (flip) {
+                            const double t1 = __dsub_rn(1.0, x2), t2 = __dsub_rn(1.0, x1);
+                            x1 = t1;
+                            x2 = t2;
+                        }
+                        double2 *ob = reinterpret_cast<double2 *>(p.out_boxes) + 2 * (out0 + pos);
+                        ob[0] = make_double2(x1, y1);
+                        ob[1] = make_double2(x2, y2);
+                    }
+                }
+                if (t >= count) {
+                    if (p.out_patch_boxes)
+                        reinterpret_cast<float4 *>(p.out_patch_boxes)[out0 + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.out_scores) p.out_scores[out0 + t] = 0.f;
+                    if (p.out_idx) p.out_idx[out0 + t] = -1;
+                    if (p.out_boxes) {
+                        double2 *ob = reinterpret_cast<double2 *>(p.out_boxes) + 2 * (out0 + t);
+                        ob[0] = make_double2(0., 0.);
+                        ob[1] = make_double2(0., 0.);
+                    }
+                }
+            }
+        }
+        if (tid == 0 && p.out_count) p.out_count[b] = count;
+        __syncthreads();   // shared state is reused by the next image
+    }
+}
+
+template <int NWARPS>
+static int launch_detect(const DetectParams &p, size_t smem, cudaStream_t st) {
+    auto kern = mbx_detect_kernel<NWARPS>;
+    static thread_local size_t configured = 0;
+    static thread_local int occ = 0;
+    if (smem > configured || occ == 0) {
+        if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    static_cast<int>(smem)),
+                               "cudaFuncSetAttribute(detect)"))
+            return e;
+        configured = smem;
+        occ = 0;
+    }
+    static thread_local size_t occ_smem = 0;
+    if (occ == 0 || occ_smem != smem) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NWARPS * 32, smem);
+        if (occ < 1) occ = 1;
+        occ_smem = smem;
+    }
+    int grid = sm_count() * occ;
+    if (grid > p.B) grid = p.B;
+    kern<<<grid, NWARPS * 32, smem, st>>>(p);
+    return check_cuda(cudaGetLastError(), "launch mbx_detect_kernel");
+}
+
+}  // namespace mbx
+
+using namespace mbx;
+
+extern "C" size_t mbx_detect_workspace_bytes(int B, int P, int k_max) {
+    (void)B;
+    (void)P;
+    (void)k_max;
+    return 256;   // the detect path needs no global scratch; kept in the ABI for symmetry
+}
+
+extern "C" int mbx_detect(const float *locations, const float *confidences, const float *priors,
+                          const float *restrictions, const int32_t *max_to_keep, const int32_t *offsets,
+                          const int32_t *patch_dims, const int32_t *image_dims, const int32_t *is_flipped, int B,
+                          int P, int k_max, float nms_iou, unsigned flags, double *out_boxes,
+                          float *out_patch_boxes, float *out_scores, int32_t *out_prior_idx, int32_t *out_count,
+                          void *workspace, size_t workspace_bytes, void *stream) {
+    (void)workspace;
+    (void)workspace_bytes;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (B < 0 || P <= 0 || k_max <= 0) {
+        set_error("mbx_detect: bad sizes B=%d P=%d k_max=%d", B, P, k_max);
+        return MBX_E_ARG;
+    }
+    if (B == 0) return 0;
+    if (!locations || !confidences || !priors) {
+        set_error("mbx_detect: null input pointer");
+        return MBX_E_ARG;
+    }
+    if ((image_dims != nullptr) != (patch_dims != nullptr) || (image_dims != nullptr) != (offsets != nullptr)) {
+        set_error("mbx_detect: offsets, patch_dims and image_dims must be given together");
+        return MBX_E_ARG;
+    }
+    auto mis16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) != 0; };
+    if (mis16(locations) || mis16(priors) || mis16(restrictions) || mis16(out_boxes) || mis16(out_patch_boxes)) {
+        set_error("mbx_detect: pointers must be 16-byte aligned");
+        return MBX_E_ARG;
+    }
+    if (k_max > 1024) {
+        set_error("mbx_detect: k_max=%d > 1024", k_max);
+        return MBX_E_TOO_LARGE;
+    }
+    DetectParams p;
+    p.locations = locations;
+    p.confidences = confidences;
+    p.priors = priors;
+    p.restrictions = restrictions;
+    p.max_to_keep = max_to_keep;
+    p.offsets = offsets;
+    p.patch_dims = patch_dims;
+    p.image_dims = image_dims;
+    p.is_flipped = is_flipped;
+    p.B = B;
+    p.P = P;
+    p.k_max = k_max;
+    int n2 = 64;
+    while (n2 < P) n2 <<= 1;
+    p.n2 = n2;
+    p.nms_iou = nms_iou;
+    p.flags = flags;
+    p.out_boxes = out_boxes;
+    p.out_patch_boxes = out_patch_boxes;
+    p.out_scores = out_scores;
+    p.out_idx = out_prior_idx;
+    p.out_count = out_count;
+    const size_t smem = dcarve(nullptr, nullptr, P, n2, k_max, nms_iou >= 0.0f);
+    if (smem > static_cast<size_t>(max_smem_optin())) {
+        set_error("mbx_detect: P=%d k_max=%d needs %zu bytes of shared memory per CTA (max %d)", P, k_max, smem,
+                  max_smem_optin());
+        return MBX_E_TOO_LARGE;
+    }
+    int nwarps = static_cast<int>((flags >> MBX_FLAG_WARPS_SHIFT) & 0xffu);
+    if (nwarps == 0) nwarps = 8;
+    switch (nwarps) {
+        case 4: return launch_detect<4>(p, smem, st);
+        case 8: return launch_detect<8>(p, smem, st);
+        case 16: return launch_detect<16>(p, smem, st);
+        default:
+            set_error("mbx_detect: forced warps must be 4, 8 or 16");
+            return MBX_E_ARG;
+    }
+}

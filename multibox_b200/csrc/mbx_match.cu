@@ -1,0 +1,707 @@
+// multibox_b200 -- GT->prior optimal matching fused with the multibox loss
+// forward/backward, one CTA per image (persistent grid), sm_100a.
+//
+// What it replaces (reference = gvanhorn38/multibox):
+//   loss.py:21-25   log terms                      -> nplogf() at load time
+//   loss.py:33-35   cost matrix C[P, n_b] (fp64)   -> never materialised: C(p, j) is
+//                                                     recomputed in registers with the
+//                                                     reference's fp32 operation order
+//   loss.py:40      scipy linear_sum_assignment    -> shortest-augmenting-path solver
+//                                                     (Crouse 2016, the algorithm scipy >= 1.4
+//                                                     ships) on the transposed problem
+//                                                     (rows = GT, columns = priors), same
+//                                                     scan order and tie rule
+//   loss.py:44-53   mask + stacked GT              -> epilogue
+//   loss.py:67-74   prior add, epsilon add         -> at load time
+//   loss.py:88-101  partition + the two losses     -> epilogue (fp64 accumulation)
+//   TF autodiff     gradients                      -> epilogue
+//   model.py:322    sigmoid (MBX_FLAG_LOGITS)      -> at load time
+//
+// Data layout in shared memory (per CTA, one image at a time):
+//   priors   float4[P]  staged ONCE per CTA with a TMA bulk copy (cp.async.bulk)
+//   loc      float4[P]  absolute predicted boxes (offset + prior)
+//   spc      double[P]  shortest path cost of each column in the current augmentation
+//   v        double[P]  column duals
+//   conf/lc/l1 float[P] confidence (+eps), log(c), log(clamp(1-c))
+//   path,row4col int16[P]; sc uint8[P] (column already scanned in this augmentation)
+//   gt float4[M], u double[M], col4row int[M], removal log int[M] x2
+// Every thread owns the columns j = tid, tid+T, ... so all per-column traffic is
+// conflict-free and needs no barrier; one __syncthreads per Dijkstra step
+// (the block-wide arg-min) and three per augmentation.
+#include <math_constants.h>
+
+#include "mbx_common.cuh"
+
+namespace mbx {
+
+struct MatchParams {
+    const float *locations, *confidences, *gt, *priors;
+    const int32_t *num_gt;
+    int B, P, M;
+    float alpha;
+    unsigned flags;
+    int32_t *mask, *gt_idx;
+    float *stacked;
+    int32_t *n_stacked;
+    float *d_loc, *d_conf, *conf_out, *results;
+    // workspace
+    double *partials;        // [B][2]
+    int32_t *img_matched;    // [B]
+    int32_t *stk_offsets;    // [B+1] exclusive scan of num_gt
+    unsigned *ticket;        // [1]
+    unsigned *status;        // [1]
+};
+
+constexpr int kTieBit = 1 << 30;
+constexpr int kNoCol = kTieBit - 1;
+
+struct Cand {
+    double v;
+    int j;   // column | kTieBit
+};
+
+__device__ __forceinline__ Cand cand_min(Cand a, Cand b) {
+    if (b.v < a.v) return b;
+    if (a.v < b.v) return a;
+    int ja = a.j & ~kTieBit, jb = b.j & ~kTieBit;
+    Cand r;
+    r.v = a.v;
+    r.j = (ja < jb ? ja : jb) | kTieBit;
+    return r;
+}
+
+__device__ __forceinline__ Cand warp_cand_min(Cand c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Cand t;
+        t.v = __shfl_xor_sync(0xffffffffu, c.v, o);
+        t.j = __shfl_xor_sync(0xffffffffu, c.j, o);
+        c = cand_min(c, t);
+    }
+    return c;
+}
+
+// fp32 cost of (prior box, gt box) in the reference's numpy operation order
+// (loss.py:35): (alpha/2) * (sqrt(((d0^2+d1^2)+d2^2)+d3^2))**2 - log_c + log_1mc
+__device__ __forceinline__ float cost32(float4 l, float4 g, float half_alpha, float lc, float l1) {
+    float d0 = __fsub_rn(l.x, g.x), d1 = __fsub_rn(l.y, g.y), d2 = __fsub_rn(l.z, g.z), d3 = __fsub_rn(l.w, g.w);
+    float s = __fmul_rn(d0, d0);
+    s = __fadd_rn(s, __fmul_rn(d1, d1));
+    s = __fadd_rn(s, __fmul_rn(d2, d2));
+    s = __fadd_rn(s, __fmul_rn(d3, d3));
+    float nrm = __fsqrt_rn(s);
+    float c = __fmul_rn(half_alpha, __fmul_rn(nrm, nrm));
+    c = __fsub_rn(c, lc);
+    c = __fadd_rn(c, l1);
+    return c;
+}
+
+struct Smem {
+    float4 *priors, *loc, *gt;
+    double *spc, *v, *u, *red;
+    float *conf, *lc, *l1;
+    int *col4row, *rm_col, *rm_idx, *pj, *ri;
+    double *pv;
+    unsigned long long *pk;
+    short *path, *row4col;
+    unsigned char *sc;
+    uint64_t *bar;
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Shared-memory carve-up; identical on host (size query) and device.
+__host__ __device__ inline size_t carve(Smem *s, unsigned char *base, int P, int M, int nwarps, bool has_priors) {
+    size_t o = 0;
+    auto take = [&](size_t bytes, size_t al) {
+        o = align_up(o, al);
+        size_t r = o;
+        o += bytes;
+        return r;
+    };
+    size_t o_pri = take(has_priors ? sizeof(float4) * P : 0, 16);
+    size_t o_loc = take(sizeof(float4) * P, 16);
+    size_t o_gt = take(sizeof(float4) * (M > 0 ? M : 1), 16);
+    size_t o_spc = take(sizeof(double) * P, 8);
+    size_t o_v = take(sizeof(double) * P, 8);
+    size_t o_u = take(sizeof(double) * (M > 0 ? M : 1), 8);
+    size_t o_red = take(sizeof(double) * 2 * nwarps, 8);
+    size_t o_pv = take(sizeof(double) * 2 * nwarps, 8);
+    size_t o_pk = take(sizeof(unsigned long long) * nwarps, 8);
+    size_t o_bar = take(sizeof(uint64_t), 8);
+    size_t o_conf = take(sizeof(float) * P, 4);
+    size_t o_lc = take(sizeof(float) * P, 4);
+    size_t o_l1 = take(sizeof(float) * P, 4);
+    size_t o_c4r = take(sizeof(int) * (M > 0 ? M : 1), 4);
+    size_t o_rmc = take(sizeof(int) * (M + 1), 4);
+    size_t o_rmi = take(sizeof(int) * (M + 1), 4);
+    size_t o_pj = take(sizeof(int) * 2 * nwarps, 4);
+    size_t o_ri = take(sizeof(int) * nwarps, 4);
+    size_t o_path = take(sizeof(short) * P, 2);
+    size_t o_r4c = take(sizeof(short) * P, 2);
+    size_t o_sc = take(P, 1);
+    if (s) {
+        s->priors = reinterpret_cast<float4 *>(base + o_pri);
+        s->loc = reinterpret_cast<float4 *>(base + o_loc);
+        s->gt = reinterpret_cast<float4 *>(base + o_gt);
+        s->spc = reinterpret_cast<double *>(base + o_spc);
+        s->v = reinterpret_cast<double *>(base + o_v);
+        s->u = reinterpret_cast<double *>(base + o_u);
+        s->red = reinterpret_cast<double *>(base + o_red);
+        s->pv = reinterpret_cast<double *>(base + o_pv);
+        s->pk = reinterpret_cast<unsigned long long *>(base + o_pk);
+        s->bar = reinterpret_cast<uint64_t *>(base + o_bar);
+        s->conf = reinterpret_cast<float *>(base + o_conf);
+        s->lc = reinterpret_cast<float *>(base + o_lc);
+        s->l1 = reinterpret_cast<float *>(base + o_l1);
+        s->col4row = reinterpret_cast<int *>(base + o_c4r);
+        s->rm_col = reinterpret_cast<int *>(base + o_rmc);
+        s->rm_idx = reinterpret_cast<int *>(base + o_rmi);
+        s->pj = reinterpret_cast<int *>(base + o_pj);
+        s->ri = reinterpret_cast<int *>(base + o_ri);
+        s->path = reinterpret_cast<short *>(base + o_path);
+        s->row4col = reinterpret_cast<short *>(base + o_r4c);
+        s->sc = base + o_sc;
+    }
+    return align_up(o, 16);
+}
+
+// Position of column j in scipy's `remaining` list after the first R removals of
+// the current augmentation (list filled in reverse, removal = swap with last).
+__device__ __forceinline__ int replay_pos(int j, int R, int P, const int *rm_idx) {
+    int pos = P - 1 - j, nrem = P;
+    for (int k = 0; k < R; ++k) {
+        --nrem;
+        if (pos == nrem) pos = rm_idx[k];
+    }
+    return pos;
+}
+
+// exclusive scan of clamp(num_gt, 0, M) -> offsets[B+1]; one CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) mbx_scan_num_gt_kernel(const int32_t *num_gt, int B, int M,
+                                                               int32_t *offsets, int32_t *n_stacked) {
+    __shared__ int warp_excl[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < B; base += 1024) {
+        const int i = base + tid;
+        int x = 0;
+        if (i < B) {
+            x = num_gt[i];
+            x = x < 0 ? 0 : (x > M ? M : x);
+        }
+        int inc = x;   // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_excl[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            const int tot = warp_excl[lane];
+            int ti = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int q = __shfl_up_sync(0xffffffffu, ti, o);
+                if (lane >= o) ti += q;
+            }
+            warp_excl[lane] = ti - tot;
+        }
+        __syncthreads();
+        const int excl = carry + warp_excl[w] + inc - x;
+        if (i < B) offsets[i] = excl;
+        __syncthreads();
+        if (tid == 1023) carry = excl + x;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        offsets[B] = carry;
+        if (n_stacked) *n_stacked = carry;
+    }
+}
+
+template <int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_kernel(const MatchParams p) {
+    constexpr int T = NWARPS * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem s;
+    const bool boundary = (p.flags & MBX_FLAG_BOUNDARY) != 0;
+    const bool logits = (p.flags & MBX_FLAG_LOGITS) != 0;
+    const bool has_priors = !boundary;
+    carve(&s, smem_raw, p.P, p.M, NWARPS, has_priors);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = p.P, M = p.M;
+    const float half_alpha = __fdiv_rn(p.alpha, 2.0f);   // (alpha / 2.) in fp32, loss.py:35
+    const double INF = CUDART_INF;
+    unsigned status = 0;
+
+    // ---- priors: one TMA bulk copy per CTA, reused for every image this CTA solves
+    if (has_priors) {
+        if (tid == 0) {
+            mbar_init(s.bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(s.bar, static_cast<uint32_t>(sizeof(float4) * P));
+            bulk_copy_g2s(s.priors, p.priors, static_cast<uint32_t>(sizeof(float4) * P), s.bar);
+        }
+    }
+    bool priors_ready = !has_priors;
+    int pbuf = 0;
+
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+        int n = p.num_gt[b];
+        if (n < 0 || n > M) {
+            status |= MBX_STATUS_BAD_NUM_GT;
+            n = n < 0 ? 0 : M;
+        }
+        const size_t row0 = static_cast<size_t>(b) * P;
+        if (!priors_ready) {
+            mbar_wait(s.bar, 0);
+            priors_ready = true;
+        }
+        // ---- load + elementwise prologue (loss.py:67-74, 21-25; model.py:322)
+        const float4 *gl = reinterpret_cast<const float4 *>(p.locations) + row0;
+        for (int j = tid; j < P; j += T) {
+            float4 l = ld_stream_f4(gl + j);
+            if (has_priors) {
+                float4 q = s.priors[j];
+                l.x = __fadd_rn(l.x, q.x);
+                l.y = __fadd_rn(l.y, q.y);
+                l.z = __fadd_rn(l.z, q.z);
+                l.w = __fadd_rn(l.w, q.w);
+            }
+            s.loc[j] = l;
+            float c = ld_stream_f(p.confidences + row0 + j);
+            if (logits) {
+                c = sigmoidf_(c);
+                if (p.conf_out) p.conf_out[row0 + j] = c;
+            }
+            s.conf[j] = c;                                  // pre-epsilon value (sigmoid output)
+            if (!boundary) c = __fadd_rn(c, kEps32);        // loss.py:74
+            s.lc[j] = nplogf(c);
+            float v = __fsub_rn(1.0f, c);
+            if (v > 1.0f) v = 1.0f;
+            if (v <= 0.0f) v = kEps32;
+            s.l1[j] = nplogf(v);
+            s.v[j] = 0.0;
+            s.row4col[j] = -1;
+            s.sc[j] = 0;
+        }
+        const float4 *gg = reinterpret_cast<const float4 *>(p.gt) + static_cast<size_t>(b) * M;
+        for (int i = tid; i < n; i += T) {
+            s.gt[i] = gg[i];
+            s.u[i] = 0.0;
+            s.col4row[i] = -1;
+        }
+        __syncthreads();
+
+        // ---- one shortest augmenting path per GT row
+        bool failed = false;
+        for (int cur = 0; cur < n && !failed; ++cur) {
+            int i = cur, R = 0;
+            double min_val = 0.0;
+            for (;;) {
+                const float4 g = s.gt[i];
+                const double ui = s.u[i];
+                const bool first = (R == 0);
+                Cand best;
+                best.v = INF;
+                best.j = kNoCol;
+                for (int j = tid; j < P; j += T) {
+                    if (s.sc[j]) continue;
+                    float c32 = cost32(s.loc[j], g, half_alpha, s.lc[j], s.l1[j]);
+                    if (c32 != c32 || c32 == -CUDART_INF_F) status |= MBX_STATUS_INVALID_COST;
+                    double r = __dsub_rn(__dsub_rn(__dadd_rn(min_val, static_cast<double>(c32)), ui), s.v[j]);
+                    double sp = first ? INF : s.spc[j];
+                    bool upd = r < sp;
+                    if (upd) {
+                        sp = r;
+                        s.path[j] = static_cast<short>(i);
+                    }
+                    if (upd || first) s.spc[j] = sp;
+                    if (sp < best.v) {
+                        best.v = sp;
+                        best.j = j;
+                    } else if (sp == best.v) {
+                        best.j |= kTieBit;
+                    }
+                }
+                // block-wide arg-min (value, lowest column, tie flag); one barrier
+                best = warp_cand_min(best);
+                if (NWARPS > 1) {
+                    if (lane == 0) {
+                        s.pv[pbuf * NWARPS + warp] = best.v;
+                        s.pj[pbuf * NWARPS + warp] = best.j;
+                    }
+                    __syncthreads();
+                    best.v = s.pv[pbuf * NWARPS];
+                    best.j = s.pj[pbuf * NWARPS];
+#pragma unroll
+                    for (int w = 1; w < NWARPS; ++w) {
+                        Cand t;
+                        t.v = s.pv[pbuf * NWARPS + w];
+                        t.j = s.pj[pbuf * NWARPS + w];
+                        best = cand_min(best, t);
+                    }
+                    pbuf ^= 1;
+                }
+                min_val = best.v;
+                if (!(min_val < INF)) {   // infeasible (scipy raises ValueError)
+                    status |= MBX_STATUS_INFEASIBLE;
+                    failed = true;
+                    break;
+                }
+                int jstar = best.j & ~kTieBit;
+                if (best.j & kTieBit) {
+                    // scipy's tie rule (rare path): among the columns at the minimum, the LAST
+                    // unassigned one in `remaining` order wins, else the FIRST assigned one.
+                    unsigned long long key = ~0ull;
+                    for (int j = tid; j < P; j += T) {
+                        if (s.sc[j] || !(s.spc[j] == min_val)) continue;
+                        int pos = replay_pos(j, R, P, s.rm_idx);
+                        unsigned k2 = (s.row4col[j] < 0) ? static_cast<unsigned>(P - 1 - pos)
+                                                         : static_cast<unsigned>(P + pos);
+                        unsigned long long k = (static_cast<unsigned long long>(k2) << 32) | static_cast<unsigned>(j);
+                        key = k < key ? k : key;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o);
+                        key = t < key ? t : key;
+                    }
+                    if (NWARPS > 1) {
+                        __syncthreads();
+                        if (lane == 0) s.pk[warp] = key;
+                        __syncthreads();
+                        key = s.pk[0];
+#pragma unroll
+                        for (int w = 1; w < NWARPS; ++w) key = s.pk[w] < key ? s.pk[w] : key;
+                    }
+                    jstar = static_cast<int>(key & 0xffffffffu);
+                }
+                const int pos = replay_pos(jstar, R, P, s.rm_idx);
+                const int r4c = s.row4col[jstar];
+                if (tid == 0) {
+                    s.rm_col[R] = jstar;
+                    s.rm_idx[R] = pos;
+                }
+                if ((jstar % T) == tid) s.sc[jstar] = 1;
+                ++R;
+                if (r4c < 0) break;   // jstar is the sink
+                i = r4c;
+                if (NWARPS == 1) __syncwarp();
+            }
+            __syncthreads();
+            if (failed) break;
+            // ---- dual update (u, v) over the scanned rows / columns
+            for (int k = tid; k < R; k += T) {
+                const int j = s.rm_col[k];
+                const double delta = __dsub_rn(min_val, s.spc[j]);
+                s.v[j] = __dsub_rn(s.v[j], delta);
+                if (k < R - 1) {
+                    const int row = s.row4col[j];
+                    s.u[row] = __dadd_rn(s.u[row], delta);
+                }
+                s.sc[j] = 0;
+            }
+            if (tid == 0) s.u[cur] = __dadd_rn(s.u[cur], min_val);
+            __syncthreads();
+            // ---- augment along the path
+            if (tid == 0) {
+                int j = s.rm_col[R - 1];
+                for (;;) {
+                    const int r = s.path[j];
+                    s.row4col[j] = static_cast<short>(r);
+                    const int t = s.col4row[r];
+                    s.col4row[r] = j;
+                    j = t;
+                    if (r == cur) break;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- epilogue: mask, matched GT index, loss terms, gradients
+        double acc_sq = 0.0, acc_conf = 0.0;
+        int n_match = 0;
+        for (int j = tid; j < P; j += T) {
+            const int r = s.row4col[j];
+            if (p.mask) p.mask[row0 + j] = r >= 0 ? 1 : 0;
+            if (p.gt_idx) p.gt_idx[row0 + j] = r;
+            n_match += r >= 0;
+            {
+                const float c = boundary ? s.conf[j] : __fadd_rn(s.conf[j], kEps32);
+                float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);
+                float dc;
+                if (r >= 0) {
+                    const float4 l = s.loc[j], g = s.gt[r];
+                    const float d0 = __fsub_rn(l.x, g.x), d1 = __fsub_rn(l.y, g.y), d2 = __fsub_rn(l.z, g.z),
+                                d3 = __fsub_rn(l.w, g.w);
+                    acc_sq += static_cast<double>(__fmul_rn(d0, d0));
+                    acc_sq += static_cast<double>(__fmul_rn(d1, d1));
+                    acc_sq += static_cast<double>(__fmul_rn(d2, d2));
+                    acc_sq += static_cast<double>(__fmul_rn(d3, d3));
+                    dl = make_float4(__fmul_rn(p.alpha, d0), __fmul_rn(p.alpha, d1), __fmul_rn(p.alpha, d2),
+                                     __fmul_rn(p.alpha, d3));
+                    acc_conf -= static_cast<double>(s.lc[j]);
+                    dc = __fdiv_rn(-1.0f, c);
+                } else {
+                    const float one_m = __fsub_rn(1.0f, c);
+                    const float arg = __fadd_rn(one_m, kEps32);
+                    float vcl = one_m;
+                    if (vcl > 1.0f) vcl = 1.0f;
+                    if (vcl <= 0.0f) vcl = kEps32;
+                    const float la = (arg == vcl) ? s.l1[j] : nplogf(arg);
+                    acc_conf -= static_cast<double>(la);
+                    dc = __fdiv_rn(1.0f, arg);
+                }
+                if (logits) {
+                    const float s0 = s.conf[j];   // d sigmoid / d logit = s (1 - s)
+                    dc = __fmul_rn(dc, __fmul_rn(s0, __fsub_rn(1.0f, s0)));
+                }
+                if (p.d_loc) st_stream_f4(reinterpret_cast<float4 *>(p.d_loc) + row0 + j, dl);
+                if (p.d_conf) p.d_conf[row0 + j] = dc;
+            }
+        }
+        // stacked GT rows in ascending prior order: rank by counting (n <= M is small)
+        if (p.stacked && !failed) {
+            const int off = p.stk_offsets[b];
+            for (int i = tid; i < n; i += T) {
+                const int pi = s.col4row[i];
+                int rank = 0;
+                for (int q = 0; q < n; ++q) rank += s.col4row[q] < pi;
+                reinterpret_cast<float4 *>(p.stacked)[off + rank] = s.gt[i];
+            }
+        }
+        {
+            acc_sq = warp_sum(acc_sq);
+            acc_conf = warp_sum(acc_conf);
+            n_match = __reduce_add_sync(0xffffffffu, n_match);
+            __syncthreads();   // s.red reuse across images
+            if (lane == 0) {
+                s.red[warp] = acc_sq;
+                s.red[NWARPS + warp] = acc_conf;
+                s.ri[warp] = n_match;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double a = 0.0, c = 0.0;
+                int m = 0;
+                for (int w = 0; w < NWARPS; ++w) {
+                    a += s.red[w];
+                    c += s.red[NWARPS + w];
+                    m += s.ri[w];
+                }
+                p.partials[2 * b] = a;
+                p.partials[2 * b + 1] = c;
+                p.img_matched[b] = m;
+            }
+        }
+        __syncthreads();   // shared state is reused by the next image
+    }
+
+    if (status) atomicOr(p.status, status);
+
+    // ---- last CTA to finish reduces the per-image partials in a fixed order
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned t = atomicAdd(p.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double a = 0.0, c = 0.0;
+    long long m = 0;
+    for (int b = tid; b < p.B; b += T) {
+        a += __ldcg(p.partials + 2 * b);
+        c += __ldcg(p.partials + 2 * b + 1);
+        m += __ldcg(p.img_matched + b);
+    }
+    a = warp_sum(a);
+    c = warp_sum(c);
+    double md = warp_sum(static_cast<double>(m));
+    if (lane == 0) {
+        s.red[warp] = a;
+        s.red[NWARPS + warp] = c;
+        s.pv[warp] = md;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double A = 0.0, C = 0.0, Mt = 0.0;
+        for (int w = 0; w < NWARPS; ++w) {
+            A += s.red[w];
+            C += s.red[NWARPS + w];
+            Mt += s.pv[w];
+        }
+        const double loc_loss = static_cast<double>(p.alpha) * (A / 2.0);   // loss.py:100
+        const unsigned st = atomicOr(p.status, 0u);
+        p.results[0] = static_cast<float>(loc_loss);
+        p.results[1] = static_cast<float>(C);
+        p.results[2] = static_cast<float>(st);
+        p.results[3] = static_cast<float>(Mt);
+        reinterpret_cast<double *>(p.results)[2] = loc_loss;
+        reinterpret_cast<double *>(p.results)[3] = C;
+        *p.ticket = 0u;    // workspace reusable by the next launch
+        *p.status = 0u;
+    }
+}
+
+struct WsLayout {
+    size_t partials, img_matched, offsets, ticket, status, total;
+};
+static WsLayout ws_layout(int B) {
+    WsLayout w;
+    size_t o = 0;
+    w.ticket = o;
+    o += 8;
+    w.status = o;
+    o += 8;
+    w.partials = o;
+    o += sizeof(double) * 2 * static_cast<size_t>(B);
+    w.img_matched = o;
+    o += sizeof(int32_t) * static_cast<size_t>(B);
+    o = align_up(o, 16);
+    w.offsets = o;
+    o += sizeof(int32_t) * (static_cast<size_t>(B) + 1);
+    w.total = align_up(o, 256);
+    return w;
+}
+
+template <int NWARPS>
+static int launch_match(const MatchParams &p, size_t smem, int grid, cudaStream_t st) {
+    auto kern = mbx_match_loss_kernel<NWARPS>;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    static_cast<int>(smem)),
+                               "cudaFuncSetAttribute(match)"))
+            return e;
+        configured = smem;
+    }
+    kern<<<grid, NWARPS * 32, smem, st>>>(p);
+    return check_cuda(cudaGetLastError(), "launch mbx_match_loss_kernel");
+}
+
+template <int NWARPS>
+static int occupancy(size_t smem) {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mbx_match_loss_kernel<NWARPS>, NWARPS * 32, smem);
+    return nb;
+}
+
+}  // namespace mbx
+
+using namespace mbx;
+
+extern "C" size_t mbx_match_workspace_bytes(int B, int P, int M) {
+    (void)P;
+    (void)M;
+    return ws_layout(B < 1 ? 1 : B).total;
+}
+
+extern "C" int mbx_match_loss(const float *locations, const float *confidences, const float *gt_bboxes,
+                              const int32_t *num_gt, const float *priors, int B, int P, int M, float alpha,
+                              unsigned flags, int32_t *mask, int32_t *matched_gt_idx, float *stacked_gt,
+                              int32_t *n_stacked, float *d_locations, float *d_confidences,
+                              float *confidences_out, float *results, void *workspace, size_t workspace_bytes,
+                              void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (B < 0 || P <= 0 || M < 0) {
+        set_error("mbx_match_loss: bad sizes B=%d P=%d M=%d", B, P, M);
+        return MBX_E_ARG;
+    }
+    if (B == 0) return 0;
+    const bool boundary = (flags & MBX_FLAG_BOUNDARY) != 0;
+    if (boundary && (flags & MBX_FLAG_LOGITS)) {
+        set_error("mbx_match_loss: MBX_FLAG_BOUNDARY and MBX_FLAG_LOGITS are exclusive");
+        return MBX_E_ARG;
+    }
+    if (!locations || !confidences || !num_gt || (M > 0 && !gt_bboxes) || (!boundary && !priors) || !workspace ||
+        !results) {
+        set_error("mbx_match_loss: null input / results / workspace pointer");
+        return MBX_E_ARG;
+    }
+    auto mis16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) != 0; };
+    if (mis16(locations) || mis16(gt_bboxes) || mis16(priors) || mis16(stacked_gt) || mis16(d_locations) ||
+        mis16(results) || mis16(workspace)) {
+        set_error("mbx_match_loss: pointers must be 16-byte aligned");
+        return MBX_E_ARG;
+    }
+    if (M > P || M > 32767 || P >= kNoCol) {
+        set_error("mbx_match_loss: need M <= P and M <= 32767 (got P=%d M=%d)", P, M);
+        return MBX_E_TOO_LARGE;
+    }
+    const WsLayout wl = ws_layout(B);
+    if (workspace_bytes < wl.total) {
+        set_error("mbx_match_loss: workspace %zu < %zu bytes", workspace_bytes, wl.total);
+        return MBX_E_WORKSPACE;
+    }
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    MatchParams p;
+    p.locations = locations;
+    p.confidences = confidences;
+    p.gt = gt_bboxes;
+    p.priors = priors;
+    p.num_gt = num_gt;
+    p.B = B;
+    p.P = P;
+    p.M = M;
+    p.alpha = alpha;
+    p.flags = flags;
+    p.mask = mask;
+    p.gt_idx = matched_gt_idx;
+    p.stacked = stacked_gt;
+    p.n_stacked = n_stacked;
+    p.d_loc = d_locations;
+    p.d_conf = d_confidences;
+    p.conf_out = confidences_out;
+    p.results = results;
+    p.partials = reinterpret_cast<double *>(ws + wl.partials);
+    p.img_matched = reinterpret_cast<int32_t *>(ws + wl.img_matched);
+    p.stk_offsets = reinterpret_cast<int32_t *>(ws + wl.offsets);
+    p.ticket = reinterpret_cast<unsigned *>(ws + wl.ticket);
+    p.status = reinterpret_cast<unsigned *>(ws + wl.status);
+
+    int nwarps = static_cast<int>((flags >> MBX_FLAG_WARPS_SHIFT) & 0xffu);
+    if (nwarps == 0) nwarps = P <= 256 ? 2 : (P <= 1024 ? 4 : 8);
+    if (nwarps != 1 && nwarps != 2 && nwarps != 4 && nwarps != 8) {
+        set_error("mbx_match_loss: forced warps must be 1, 2, 4 or 8");
+        return MBX_E_ARG;
+    }
+    const size_t smem = carve(nullptr, nullptr, P, M, nwarps, !boundary);
+    if (smem > static_cast<size_t>(max_smem_optin())) {
+        set_error("mbx_match_loss: P=%d M=%d needs %zu bytes of shared memory per CTA (max %d)", P, M, smem,
+                  max_smem_optin());
+        return MBX_E_TOO_LARGE;
+    }
+    if (stacked_gt || n_stacked) {
+        mbx_scan_num_gt_kernel<<<1, 1024, 0, st>>>(num_gt, B, M, p.stk_offsets, n_stacked);
+        if (int e = check_cuda(cudaGetLastError(), "launch mbx_scan_num_gt_kernel")) return e;
+    }
+    int occ = 1;
+    switch (nwarps) {
+        case 1: occ = occupancy<1>(smem); break;
+        case 2: occ = occupancy<2>(smem); break;
+        case 4: occ = occupancy<4>(smem); break;
+        default: occ = occupancy<8>(smem); break;
+    }
+    if (occ < 1) occ = 1;
+    int grid = sm_count() * occ;
+    if (grid > B) grid = B;
+    int rc;
+    switch (nwarps) {
+        case 1: rc = launch_match<1>(p, smem, grid, st); break;
+        case 2: rc = launch_match<2>(p, smem, grid, st); break;
+        case 4: rc = launch_match<4>(p, smem, grid, st); break;
+        default: rc = launch_match<8>(p, smem, grid, st); break;
+    }
+    return rc;
+}
