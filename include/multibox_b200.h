@@ -151,6 +151,38 @@ int mbx_detect(const float *locations, const float *confidences, const float *pr
                int32_t *out_prior_idx, int32_t *out_count,
                void *workspace, size_t workspace_bytes, void *stream);
 
+/* Batched filter_proposals (reference detect.py:74-104): order-preserving
+ * compaction of the boxes that lie inside the restriction rectangle.
+ *   bboxes [B,P,4], confidences [B,P], restrictions [B,4] (NULL = the reference's
+ *   default [0.1,0.1,0.9,0.9]) -> out_bboxes [B,P,4], out_confidences [B,P],
+ *   out_idx [B,P] int32 original index (NULL ok), out_count [B] int32.
+ * Rows >= out_count[b] are left untouched. */
+int mbx_filter_proposals(const float *bboxes, const float *confidences, const float *restrictions,
+                         int B, int P, float *out_bboxes, float *out_confidences,
+                         int32_t *out_idx, int32_t *out_count, void *stream);
+
+/* Batched convert_proposals (reference detect.py:106-131), float64 output:
+ *   bboxes [B,K,4] f32, offsets [B,2] (y,x), patch_dims [B,2] (h,w), image_dims [B,2]
+ *   (h,w) int32, is_flipped [B] int32 (NULL = 0), counts [B] int32 (NULL = K; rows >=
+ *   count are written as 0) -> out_boxes [B,K,4] float64. */
+int mbx_convert_proposals(const float *bboxes, const int32_t *offsets, const int32_t *patch_dims,
+                          const int32_t *image_dims, const int32_t *is_flipped, const int32_t *counts,
+                          int B, int K, double *out_boxes, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Diagnostics (used by the parity tests; not on the hot path)
+ * ------------------------------------------------------------------------- */
+
+/* out[i] = the kernels' float32 log of in[i] (bit-compatible with numpy's np.log
+ * on float32, which reference loss.py:21,25 calls). */
+int mbx_debug_nplog(const float *in, float *out, long long n, void *stream);
+
+/* The cost matrix of reference loss.py:33-35 for ONE image, as the matching
+ * kernel evaluates it on the fly: loc [P,4] absolute boxes, conf [P] (epsilon
+ * added), gt [n,4] -> C [P,n] float64 row-major. */
+int mbx_debug_cost_matrix(const float *loc, const float *conf, const float *gt, int P, int n,
+                          float alpha, double *C, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -344,9 +344,117 @@ static int launch_detect(const DetectParams &p, size_t smem, cudaStream_t st) {
     return check_cuda(cudaGetLastError(), "launch mbx_detect_kernel");
 }
 
+
+// ---- batched filter_proposals (detect.py:74-104): ordered compaction, one CTA per image
+__global__ void __launch_bounds__(256) mbx_filter_kernel(const float *bboxes, const float *conf,
+                                                         const float *restrictions, int B, int P,
+                                                         float *out_b, float *out_c, int32_t *out_idx,
+                                                         int32_t *out_count) {
+    __shared__ int warp_cnt[8];
+    __shared__ int base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        float4 r = make_float4(0.1f, 0.1f, 0.9f, 0.9f);   // the reference's default
+        if (restrictions) r = reinterpret_cast<const float4 *>(restrictions)[b];
+        const size_t row0 = static_cast<size_t>(b) * P;
+        if (tid == 0) base = 0;
+        __syncthreads();
+        for (int j0 = 0; j0 < P; j0 += 256) {
+            const int j = j0 + tid;
+            bool keep = false;
+            float4 l = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < P) {
+                l = ld_stream_f4(reinterpret_cast<const float4 *>(bboxes) + row0 + j);
+                keep = !((l.x < r.x) || (l.y < r.y) || (l.z > r.z) || (l.w > r.w));
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) warp_cnt[warp] = __popc(bal);
+            __syncthreads();
+            int off = base;
+            for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) tot += warp_cnt[w];
+            if (keep) {
+                const int pos = off + __popc(bal & ((1u << lane) - 1u));
+                reinterpret_cast<float4 *>(out_b)[row0 + pos] = l;
+                out_c[row0 + pos] = conf[row0 + j];
+                if (out_idx) out_idx[row0 + pos] = j;
+            }
+            __syncthreads();
+            if (tid == 0) base += tot;
+            __syncthreads();
+        }
+        if (tid == 0) out_count[b] = base;
+        __syncthreads();
+    }
+}
+
+// ---- batched convert_proposals (detect.py:106-131), float64
+__global__ void __launch_bounds__(256) mbx_convert_kernel(const float *bboxes, const int32_t *offsets,
+                                                          const int32_t *patch_dims, const int32_t *image_dims,
+                                                          const int32_t *is_flipped, const int32_t *counts, int B,
+                                                          int K, double *out) {
+    const long long total = static_cast<long long>(B) * K;
+    for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += 256ll * gridDim.x) {
+        const int b = static_cast<int>(e / K), t = static_cast<int>(e - static_cast<long long>(b) * K);
+        double x1 = 0., y1 = 0., x2 = 0., y2 = 0.;
+        if (!counts || t < counts[b]) {
+            const float4 bx = reinterpret_cast<const float4 *>(bboxes)[e];
+            const double ih = static_cast<double>(image_dims[2 * b]), iw = static_cast<double>(image_dims[2 * b + 1]);
+            const double sx = __ddiv_rn(static_cast<double>(patch_dims[2 * b + 1]), iw);
+            const double sy = __ddiv_rn(static_cast<double>(patch_dims[2 * b]), ih);
+            const double ox = __ddiv_rn(static_cast<double>(offsets[2 * b + 1]), iw);
+            const double oy = __ddiv_rn(static_cast<double>(offsets[2 * b]), ih);
+            x1 = __dadd_rn(__dmul_rn(static_cast<double>(bx.x), sx), ox);
+            y1 = __dadd_rn(__dmul_rn(static_cast<double>(bx.y), sy), oy);
+            x2 = __dadd_rn(__dmul_rn(static_cast<double>(bx.z), sx), ox);
+            y2 = __dadd_rn(__dmul_rn(static_cast<double>(bx.w), sy), oy);
+            if (is_flipped && is_flipped[b]) {
+                const double t1 = __dsub_rn(1.0, x2), t2 = __dsub_rn(1.0, x1);
+                x1 = t1;
+                x2 = t2;
+            }
+        }
+        double2 *ob = reinterpret_cast<double2 *>(out) + 2 * e;
+        ob[0] = make_double2(x1, y1);
+        ob[1] = make_double2(x2, y2);
+    }
+}
+
 }  // namespace mbx
 
 using namespace mbx;
+
+extern "C" int mbx_filter_proposals(const float *bboxes, const float *confidences, const float *restrictions,
+                                    int B, int P, float *out_bboxes, float *out_confidences, int32_t *out_idx,
+                                    int32_t *out_count, void *stream) {
+    if (B < 0 || P <= 0 || !bboxes || !confidences || !out_bboxes || !out_confidences || !out_count) {
+        set_error("mbx_filter_proposals: bad arguments");
+        return MBX_E_ARG;
+    }
+    if (B == 0) return 0;
+    int grid = B < sm_count() * 8 ? B : sm_count() * 8;
+    mbx_filter_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(bboxes, confidences, restrictions, B, P,
+                                                                           out_bboxes, out_confidences, out_idx,
+                                                                           out_count);
+    return check_cuda(cudaGetLastError(), "launch mbx_filter_kernel");
+}
+
+extern "C" int mbx_convert_proposals(const float *bboxes, const int32_t *offsets, const int32_t *patch_dims,
+                                     const int32_t *image_dims, const int32_t *is_flipped, const int32_t *counts,
+                                     int B, int K, double *out_boxes, void *stream) {
+    if (B < 0 || K < 0 || !bboxes || !offsets || !patch_dims || !image_dims || !out_boxes) {
+        set_error("mbx_convert_proposals: bad arguments");
+        return MBX_E_ARG;
+    }
+    if (B == 0 || K == 0) return 0;
+    long long total = static_cast<long long>(B) * K;
+    long long blocks = (total + 255) / 256;
+    int grid = static_cast<int>(blocks < sm_count() * 16ll ? blocks : sm_count() * 16ll);
+    mbx_convert_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(bboxes, offsets, patch_dims, image_dims,
+                                                                            is_flipped, counts, B, K, out_boxes);
+    return check_cuda(cudaGetLastError(), "launch mbx_convert_kernel");
+}
 
 extern "C" size_t mbx_detect_workspace_bytes(int B, int P, int k_max) {
     (void)B;

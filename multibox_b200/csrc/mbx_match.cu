@@ -597,9 +597,47 @@ static int occupancy(size_t smem) {
     return nb;
 }
 
+
+// ---- diagnostics -----------------------------------------------------------
+__global__ void mbx_debug_nplog_kernel(const float *in, float *out, long long n) {
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) out[i] = nplogf(in[i]);
+}
+
+__global__ void mbx_debug_cost_kernel(const float *loc, const float *conf, const float *gt, int P, int n,
+                                      float alpha, double *C) {
+    const float half_alpha = __fdiv_rn(alpha, 2.0f);
+    for (int p = blockIdx.x * 256 + threadIdx.x; p < P; p += 256 * gridDim.x) {
+        const float c = conf[p];
+        const float lc = nplogf(c);
+        float v = __fsub_rn(1.0f, c);
+        if (v > 1.0f) v = 1.0f;
+        if (v <= 0.0f) v = kEps32;
+        const float l1 = nplogf(v);
+        const float4 l = reinterpret_cast<const float4 *>(loc)[p];
+        for (int j = 0; j < n; ++j)
+            C[static_cast<size_t>(p) * n + j] =
+                static_cast<double>(cost32(l, reinterpret_cast<const float4 *>(gt)[j], half_alpha, lc, l1));
+    }
+}
+
 }  // namespace mbx
 
 using namespace mbx;
+
+extern "C" int mbx_debug_nplog(const float *in, float *out, long long n, void *stream) {
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    int grid = static_cast<int>(blocks < 148 * 16 ? blocks : 148 * 16);
+    mbx_debug_nplog_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, n);
+    return check_cuda(cudaGetLastError(), "launch mbx_debug_nplog_kernel");
+}
+
+extern "C" int mbx_debug_cost_matrix(const float *loc, const float *conf, const float *gt, int P, int n,
+                                     float alpha, double *C, void *stream) {
+    if (P <= 0 || n <= 0) return 0;
+    mbx_debug_cost_kernel<<<(P + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(loc, conf, gt, P, n, alpha, C);
+    return check_cuda(cudaGetLastError(), "launch mbx_debug_cost_kernel");
+}
 
 extern "C" size_t mbx_match_workspace_bytes(int B, int P, int M) {
     (void)P;

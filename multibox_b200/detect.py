@@ -1,0 +1,171 @@
+"""Detection post-processing -- host-side mirror of the reference's ``detect.py``
+helpers (``filter_proposals`` detect.py:74, ``convert_proposals`` detect.py:106)
+and of the per-image loop body detect.py:408-436 / eval.py:142-175, batched.
+
+Arguments are CUDA ``torch.Tensor``s; all arithmetic runs in the sm_100a
+kernels behind the C ABI (``mbx_detect``, ``mbx_filter_proposals``,
+``mbx_convert_proposals``).  There is no CPU path.
+"""
+import torch
+
+from . import _lib
+from .loss import _f32c, _i32c
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def filter_proposals(bboxes, confidences, restrictions=None):
+    """Drop-in for reference detect.py:74-104 on one image: bboxes [P,4],
+    confidences [P,1] (or [P]) -> (filtered bboxes [F,4], filtered confidences
+    [F,1]), order preserved; restrictions default [0.1,0.1,0.9,0.9].  Like the
+    reference, an empty result has shape (0,).  Synchronises (F is data dependent)."""
+    lib = _lib.load()
+    b = _f32c(bboxes, "bboxes").view(1, -1, 4)
+    P = b.shape[1]
+    conf_shape_tail = tuple(confidences.shape[1:])
+    c = _f32c(confidences, "confidences").view(1, P)
+    r = None
+    if restrictions is not None:
+        r = torch.as_tensor(restrictions, dtype=torch.float32).to(b.device).contiguous().view(1, 4)
+    ob = torch.empty_like(b)
+    oc = torch.empty_like(c)
+    cnt = torch.empty((1,), dtype=torch.int32, device=b.device)
+    rc = lib.mbx_filter_proposals(_lib.ptr(b), _lib.ptr(c), _lib.ptr(r), 1, P, _lib.ptr(ob), _lib.ptr(oc),
+                                  None, _lib.ptr(cnt), _stream(b.device))
+    _lib.check(rc, "mbx_filter_proposals")
+    n = int(cnt.item())
+    if n == 0:
+        e = torch.empty((0,), dtype=torch.float32, device=b.device)
+        return e, e.clone()
+    return ob[0, :n], oc[0, :n].view((n,) + conf_shape_tail)
+
+
+def filter_proposals_batched(bboxes, confidences, restrictions=None):
+    """bboxes [B,P,4], confidences [B,P], restrictions [B,4] -> padded
+    (bboxes [B,P,4], confidences [B,P], prior_idx [B,P] int32, count [B] int32)."""
+    lib = _lib.load()
+    b = _f32c(bboxes, "bboxes")
+    B, P = b.shape[0], b.shape[1]
+    c = _f32c(confidences, "confidences").view(B, P)
+    r = None if restrictions is None else _f32c(restrictions, "restrictions")
+    ob, oc = torch.zeros_like(b), torch.zeros_like(c)
+    oi = torch.full((B, P), -1, dtype=torch.int32, device=b.device)
+    cnt = torch.empty((B,), dtype=torch.int32, device=b.device)
+    rc = lib.mbx_filter_proposals(_lib.ptr(b), _lib.ptr(c), _lib.ptr(r), B, P, _lib.ptr(ob), _lib.ptr(oc),
+                                  _lib.ptr(oi), _lib.ptr(cnt), _stream(b.device))
+    _lib.check(rc, "mbx_filter_proposals")
+    return ob, oc, oi, cnt
+
+
+def convert_proposals(bboxes, offset, patch_dims, image_dims, is_flipped=0):
+    """Drop-in for reference detect.py:106-131 on one image: bboxes [k,4] f32,
+    offset (y,x), patch_dims (h,w), image_dims (h,w) -> float64 [k,4]."""
+    lib = _lib.load()
+    b = _f32c(bboxes, "bboxes").view(1, -1, 4)
+    K = b.shape[1]
+    dev = b.device
+
+    def i2(v):
+        return torch.as_tensor([int(v[0]), int(v[1])], dtype=torch.int32).to(dev).view(1, 2)
+
+    fl = torch.as_tensor([1 if bool(int(torch.as_tensor(is_flipped).reshape(-1)[0])) else 0],
+                         dtype=torch.int32).to(dev)
+    out = torch.empty((1, K, 4), dtype=torch.float64, device=dev)
+    rc = lib.mbx_convert_proposals(_lib.ptr(b), _lib.ptr(i2(offset)), _lib.ptr(i2(patch_dims)),
+                                   _lib.ptr(i2(image_dims)), _lib.ptr(fl), None, 1, K, _lib.ptr(out), _stream(dev))
+    _lib.check(rc, "mbx_convert_proposals")
+    return out[0]
+
+
+def postprocess(locs, confs, bbox_priors, restrictions=None, max_to_keep=None, offsets=None,
+                patch_dims=None, image_dims=None, is_flipped=None, nms_iou=None, k_max=None,
+                logits=False, want_patch_boxes=True, warps=0, out=None):
+    """The loop body of reference detect.py:408-436 for a whole batch in one
+    kernel launch (decode, clip, filter_proposals, top max_to_keep by confidence
+    with numpy's stable-argsort-then-reverse tie order, convert_proposals), plus
+    an optional greedy NMS (extension, `nms_iou`).
+
+    locs [B,P,4], confs [B,P,1], bbox_priors [P,4], restrictions [B,4] f32,
+    max_to_keep [B,1] i32, offsets/patch_dims/image_dims [B,2] i32 (y,x)/(h,w),
+    is_flipped [B,1] i32.  Returns a dict of padded device tensors:
+    boxes f64 [B,k,4] (image coordinates), patch_boxes f32 [B,k,4], scores f32
+    [B,k], prior_idx i32 [B,k] (-1 padding), count i32 [B].  No sync."""
+    lib = _lib.load()
+    loc = _f32c(locs, "locs")
+    B, P = loc.shape[0], loc.shape[1]
+    dev = loc.device
+    conf = _f32c(confs, "confs").view(B, P)
+    pri = _f32c(bbox_priors, "bbox_priors")
+    r = None if restrictions is None else _f32c(restrictions, "restrictions").view(B, 4)
+    mk = None if max_to_keep is None else _i32c(max_to_keep, "max_to_keep").view(B)
+    if k_max is None:
+        if mk is None:
+            raise ValueError("postprocess needs k_max or max_to_keep")
+        k_max = int(mk.max().item())
+    k_max = max(1, min(int(k_max), 1024))
+    conv = [offsets, patch_dims, image_dims]
+    if any(c is not None for c in conv) and not all(c is not None for c in conv):
+        raise ValueError("offsets, patch_dims and image_dims must be given together")
+    off = None if offsets is None else _i32c(offsets, "offsets").view(B, 2)
+    pd = None if patch_dims is None else _i32c(patch_dims, "patch_dims").view(B, 2)
+    imd = None if image_dims is None else _i32c(image_dims, "image_dims").view(B, 2)
+    fl = None if is_flipped is None else _i32c(is_flipped, "is_flipped").view(B)
+    out = {} if out is None else out
+
+    def buf(name, shape, dtype):
+        t = out.get(name)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            out[name] = t
+        return t
+
+    boxes = buf("boxes", (B, k_max, 4), torch.float64)
+    pboxes = buf("patch_boxes", (B, k_max, 4), torch.float32) if want_patch_boxes else None
+    scores = buf("scores", (B, k_max), torch.float32)
+    idx = buf("prior_idx", (B, k_max), torch.int32)
+    cnt = buf("count", (B,), torch.int32)
+    flags = (_lib.FLAG_LOGITS if logits else 0) | (int(warps) << _lib.FLAG_WARPS_SHIFT)
+    rc = lib.mbx_detect(_lib.ptr(loc), _lib.ptr(conf), _lib.ptr(pri), _lib.ptr(r), _lib.ptr(mk),
+                        _lib.ptr(off), _lib.ptr(pd), _lib.ptr(imd), _lib.ptr(fl),
+                        B, P, k_max, -1.0 if nms_iou is None else float(nms_iou), flags,
+                        _lib.ptr(boxes), _lib.ptr(pboxes), _lib.ptr(scores), _lib.ptr(idx), _lib.ptr(cnt),
+                        None, 0, _stream(dev))
+    _lib.check(rc, "mbx_detect")
+    return out
+
+
+def detection_results(post, image_ids):
+    """Host-side tail of the reference loop (detect.py:438-443): the list of
+    {"image_id", "bbox", "score"} rows that detect.py dumps to JSON."""
+    boxes = post["boxes"].cpu().numpy()
+    scores = post["scores"].cpu().numpy()
+    count = post["count"].cpu().numpy()
+    ids = torch.as_tensor(image_ids).cpu().numpy().reshape(-1)
+    rows = []
+    for b in range(boxes.shape[0]):
+        for k in range(int(count[b])):
+            rows.append({"image_id": int(ids[b]), "bbox": boxes[b, k].tolist(), "score": float(scores[b, k])})
+    return rows
+
+
+def eval_topk(locs, confs, bbox_priors, input_size, image_ids, k=100):
+    """reference eval.py:142-175: decode, clip, scale to pixels, descending sort,
+    top-k -> rows [img_id, x, y, w, h, score, 1] (COCO result format)."""
+    B = locs.shape[0]
+    dev = locs.device
+    zeros2 = torch.zeros((B, 2), dtype=torch.int32, device=dev)
+    size2 = torch.full((B, 2), int(input_size), dtype=torch.int32, device=dev)
+    ones2 = torch.ones((B, 2), dtype=torch.int32, device=dev)
+    post = postprocess(locs, confs, bbox_priors, restrictions=None, max_to_keep=None, offsets=zeros2,
+                       patch_dims=size2, image_dims=ones2, is_flipped=None, nms_iou=None, k_max=k)
+    boxes = post["boxes"].cpu().numpy()
+    scores = post["scores"].cpu().numpy()
+    ids = torch.as_tensor(image_ids).cpu().numpy().reshape(-1)
+    rows = []
+    for b in range(B):
+        for t in range(k):
+            x1, y1, x2, y2 = boxes[b, t]
+            rows.append([int(ids[b]), x1, y1, x2 - x1, y2 - y1, float(scores[b, t]), 1])
+    return rows

@@ -1,0 +1,244 @@
+"""Matching + multibox loss -- host-side mirror of the reference's ``loss.py``.
+
+Same function names, argument order, tensor layouts and error behaviour as the
+reference (``compute_assignments`` loss.py:8, ``add_loss`` loss.py:55), with
+CUDA ``torch.Tensor`` arguments in place of numpy arrays / TF tensors.  All
+arithmetic runs in the hand-written sm_100a kernels behind the C ABI
+(``mbx_match_loss``); this module only allocates outputs, passes pointers and
+turns the device status word into the ``ValueError`` scipy would raise at
+reference loss.py:40.  There is no CPU path.
+"""
+import torch
+
+from . import _lib
+
+SMALL_EPSILON = 1e-10   # reference loss.py:6
+
+_workspaces = {}
+
+
+def _workspace(device, nbytes):
+    """Zero-initialised scratch, one per (device, stream); grown on demand."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _f32c(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA torch.Tensor (there is no CPU path)" % name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _i32c(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA torch.Tensor (there is no CPU path)" % name)
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    return t.contiguous()
+
+
+def raise_for_status(status):
+    """Same failures, same exception type as scipy.optimize.linear_sum_assignment."""
+    status = int(status)
+    if status & _lib.STATUS_INVALID_COST:
+        raise ValueError("matrix contains invalid numeric entries")
+    if status & _lib.STATUS_INFEASIBLE:
+        raise ValueError("cost matrix is infeasible")
+    if status & _lib.STATUS_BAD_NUM_GT:
+        raise ValueError("num_gt_bboxes entry outside [0, MAX_NUM_BBOXES]")
+
+
+def match_loss_raw(locations, confidences, gt_bboxes, num_gt, priors, alpha, flags=0,
+                   want_mask=False, want_gt_idx=False, want_stacked=False, want_grads=True,
+                   want_conf_out=False, warps=0, out=None):
+    """Thin wrapper of ``mbx_match_loss`` (see include/multibox_b200.h).  Inputs
+    must already be contiguous fp32/int32 CUDA tensors; locations [B,P,4],
+    confidences [B,P].  Returns a dict of device tensors; nothing synchronises.
+    `out` may carry preallocated output tensors (same keys) to avoid allocation."""
+    lib = _lib.load()
+    B, P = locations.shape[0], locations.shape[1]
+    M = gt_bboxes.shape[1]
+    dev = locations.device
+    out = {} if out is None else out
+
+    def buf(name, want, shape, dtype):
+        if not want:
+            return None
+        t = out.get(name)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            out[name] = t
+        return t
+
+    mask = buf("mask", want_mask, (B * P,), torch.int32)
+    gt_idx = buf("matched_gt_idx", want_gt_idx, (B * P,), torch.int32)
+    stacked = buf("stacked_gt", want_stacked, (max(B * M, 1), 4), torch.float32)
+    n_stacked = buf("n_stacked", want_stacked, (1,), torch.int32)
+    d_loc = buf("d_locations", want_grads, (B, P, 4), torch.float32)
+    d_conf = buf("d_confidences", want_grads, (B, P, 1), torch.float32)
+    conf_out = buf("confidences", want_conf_out, (B, P, 1), torch.float32)
+    results = buf("results", True, (8,), torch.float32)
+    nbytes = lib.mbx_match_workspace_bytes(B, P, M)
+    ws = _workspace(dev, nbytes)
+    flags = int(flags) | (int(warps) << _lib.FLAG_WARPS_SHIFT)
+    rc = lib.mbx_match_loss(
+        _lib.ptr(locations), _lib.ptr(confidences), _lib.ptr(gt_bboxes), _lib.ptr(num_gt), _lib.ptr(priors),
+        B, P, M, float(alpha), flags,
+        _lib.ptr(mask), _lib.ptr(gt_idx), _lib.ptr(stacked), _lib.ptr(n_stacked),
+        _lib.ptr(d_loc), _lib.ptr(d_conf), _lib.ptr(conf_out), _lib.ptr(results),
+        _lib.ptr(ws), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "mbx_match_loss")
+    return out
+
+
+def compute_assignments(locations, confidences, gt_bboxes, num_gt_bboxes, batch_size, alpha,
+                        return_indices=False):
+    """Drop-in for reference loss.py:8-53 (the tf.py_func body).
+
+    locations [B*P,4] (prior already added), confidences [B*P] (epsilon already
+    added), gt_bboxes [B,M,4], num_gt_bboxes [B] int32, all CUDA tensors.
+    Returns ``[assignment_partitions int32 [B*P], stacked_gt_bboxes f32 [N,4]]``
+    (``+ [matched_gt_idx int32 [B*P]]`` with return_indices).  Raises ValueError
+    where scipy's linear_sum_assignment would.  The result shape is data
+    dependent, so this call synchronises (one 32-byte read-back)."""
+    B = int(batch_size)
+    loc = _f32c(locations, "locations")
+    conf = _f32c(confidences, "confidences")
+    P = loc.shape[0] // B                 # reference loss.py:16
+    loc = loc.view(B, P, 4)
+    conf = conf.view(B, P)
+    gt = _f32c(gt_bboxes, "gt_bboxes")
+    ng = _i32c(num_gt_bboxes, "num_gt_bboxes")
+    out = match_loss_raw(loc, conf, gt, ng, None, alpha, flags=_lib.FLAG_BOUNDARY,
+                         want_mask=True, want_gt_idx=return_indices, want_stacked=True,
+                         want_grads=False)
+    res = out["results"].cpu()
+    raise_for_status(res[2].item())
+    n = int(out["n_stacked"].item())
+    ret = [out["mask"], out["stacked_gt"][:n]]
+    if return_indices:
+        ret.append(out["matched_gt_idx"])
+    return ret
+
+
+class _AddLoss(torch.autograd.Function):
+    """Fused forward + backward: one kernel produces both losses and both
+    gradients (the matching itself is non-differentiable, as the tf.py_func at
+    reference loss.py:82 is)."""
+
+    @staticmethod
+    def forward(ctx, locations, confidences, batched_bboxes, batched_num_bboxes, bbox_priors,
+                alpha, flags, validate):
+        loc = _f32c(locations, "locations")
+        B, P = loc.shape[0], loc.shape[1]
+        conf = _f32c(confidences, "confidences").view(B, P)
+        out = match_loss_raw(loc, conf, _f32c(batched_bboxes, "batched_bboxes"),
+                             _i32c(batched_num_bboxes, "batched_num_bboxes"),
+                             _f32c(bbox_priors, "bbox_priors"), alpha, flags=flags)
+        res = out["results"]
+        if validate:
+            raise_for_status(res[2].item())
+        ctx.save_for_backward(out["d_locations"], out["d_confidences"])
+        ctx.conf_shape = confidences.shape
+        ctx.mark_non_differentiable(res)
+        return res[0], res[1], res
+
+    @staticmethod
+    def backward(ctx, g_loc, g_conf, _g_res):
+        d_loc, d_conf = ctx.saved_tensors
+        gl = d_loc * g_loc if g_loc is not None else None
+        gc = (d_conf * g_conf).view(ctx.conf_shape) if g_conf is not None else None
+        return gl, gc, None, None, None, None, None, None
+
+
+def add_loss(locations, confidences, batched_bboxes, batched_num_bboxes, bbox_priors,
+             location_loss_alpha, validate=True):
+    """Drop-in for reference loss.py:55-117.
+
+    locations [B,P,4] predicted offsets, confidences [B,P,1] post-sigmoid,
+    batched_bboxes [B,M,4], batched_num_bboxes [B] int32, bbox_priors [P,4].
+    Returns ``(location_loss, confidence_loss)`` as 0-d fp32 CUDA tensors (batch
+    sums, reference loss.py:100-101) that back-propagate to `locations` and
+    `confidences`.  With validate=True (default) the device status word is read
+    back (one sync) and the ValueError of scipy's solver is reproduced."""
+    loc_loss, conf_loss, _ = _AddLoss.apply(locations, confidences, batched_bboxes, batched_num_bboxes,
+                                            bbox_priors, float(location_loss_alpha), 0, bool(validate))
+    return loc_loss, conf_loss
+
+
+def add_loss_from_logits(locations, logits, batched_bboxes, batched_num_bboxes, bbox_priors,
+                         location_loss_alpha, validate=True):
+    """Extension: same as add_loss but takes the pre-sigmoid head output and
+    fuses reference model.py:322 into the kernel; gradients flow to the logits."""
+    loc_loss, conf_loss, _ = _AddLoss.apply(locations, logits, batched_bboxes, batched_num_bboxes,
+                                            bbox_priors, float(location_loss_alpha), _lib.FLAG_LOGITS,
+                                            bool(validate))
+    return loc_loss, conf_loss
+
+
+class MultiboxLossStep:
+    """Allocation-free training-step object: preallocated outputs, one kernel
+    launch per step, optional pinned-host staging for callers that hold HOST
+    buffers (the reference's tf.py_func boundary hands numpy arrays over).
+
+    step(...)      device tensors in, device results out (no sync)
+    step_host(...) host numpy arrays in (H2D from pinned memory), losses+status out
+                   (D2H), i.e. the end-to-end path a host caller sees.
+    """
+
+    def __init__(self, B, P, M, priors, alpha, device="cuda", logits=False, want_mask=False,
+                 want_stacked=False, warps=0):
+        self.B, self.P, self.M, self.alpha = B, P, M, float(alpha)
+        self.device = torch.device(device)
+        self.flags = _lib.FLAG_LOGITS if logits else 0
+        self.warps = warps
+        self.priors = _f32c(torch.as_tensor(priors).to(self.device), "priors")
+        self.want_mask, self.want_stacked = want_mask, want_stacked
+        self.out = {}
+        # device staging + pinned host staging for step_host
+        self.d_loc_in = torch.empty((B, P, 4), dtype=torch.float32, device=self.device)
+        self.d_conf_in = torch.empty((B, P), dtype=torch.float32, device=self.device)
+        self.d_gt_in = torch.empty((B, M, 4), dtype=torch.float32, device=self.device)
+        self.d_ng_in = torch.empty((B,), dtype=torch.int32, device=self.device)
+        self.h_loc = torch.empty((B, P, 4), dtype=torch.float32).pin_memory()
+        self.h_conf = torch.empty((B, P), dtype=torch.float32).pin_memory()
+        self.h_gt = torch.empty((B, M, 4), dtype=torch.float32).pin_memory()
+        self.h_ng = torch.empty((B,), dtype=torch.int32).pin_memory()
+        self.h_res = torch.empty((8,), dtype=torch.float32).pin_memory()
+        self.h2d_bytes = 4 * (B * P * 4 + B * P + B * M * 4 + B)
+        self.d2h_bytes = 32
+
+    def step(self, locations, confidences, gt, num_gt):
+        return match_loss_raw(locations, confidences.view(self.B, self.P), gt, num_gt, self.priors,
+                              self.alpha, flags=self.flags, want_mask=self.want_mask,
+                              want_gt_idx=self.want_mask, want_stacked=self.want_stacked,
+                              want_grads=True, warps=self.warps, out=self.out)
+
+    def step_host(self, locations, confidences, gt, num_gt, validate=True):
+        """numpy in -> (location_loss, confidence_loss) python floats out; the
+        gradients stay on the device in self.out (they feed the network's backward)."""
+        import numpy as np
+        np.copyto(self.h_loc.numpy(), locations.reshape(self.B, self.P, 4))
+        np.copyto(self.h_conf.numpy(), confidences.reshape(self.B, self.P))
+        np.copyto(self.h_gt.numpy(), gt)
+        np.copyto(self.h_ng.numpy(), num_gt)
+        return self.step_pinned(validate)
+
+    def step_pinned(self, validate=True):
+        """Same as step_host when the caller already wrote into the pinned buffers."""
+        self.d_loc_in.copy_(self.h_loc, non_blocking=True)
+        self.d_conf_in.copy_(self.h_conf, non_blocking=True)
+        self.d_gt_in.copy_(self.h_gt, non_blocking=True)
+        self.d_ng_in.copy_(self.h_ng, non_blocking=True)
+        out = self.step(self.d_loc_in, self.d_conf_in, self.d_gt_in, self.d_ng_in)
+        self.h_res.copy_(out["results"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        if validate:
+            raise_for_status(self.h_res[2].item())
+        return float(self.h_res[0]), float(self.h_res[1])

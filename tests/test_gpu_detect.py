@@ -1,0 +1,146 @@
+"""-m gpu parity tests of detection post-processing (through the C ABI) against
+the oracle and the golden rows generated from the reference's own detect.py.
+Kept-box indices and float64 converted boxes must be BIT-EXACT."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from multibox_b200 import detect, synth
+from oracle import np_oracle
+from gpu_util import dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(d, nms_iou=None, k_max=None, logits=False, warps=0):
+    out = detect.postprocess(dev(d["locations"]), dev(d["logits"] if logits else d["confidences"]),
+                             dev(d["priors"]),
+                             restrictions=dev(d["restrictions"]), max_to_keep=dev(d["max_to_keep"]),
+                             offsets=dev(d["offsets"]), patch_dims=dev(d["patch_dims"]),
+                             image_dims=dev(d["image_dims"]), is_flipped=dev(d["is_flipped"]),
+                             nms_iou=nms_iou, k_max=k_max, logits=logits, warps=warps)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def _compare(out, post):
+    counts = np.array([m["boxes"].shape[0] for m in post], dtype=np.int32)
+    assert np.array_equal(out["count"], counts)
+    for b, m in enumerate(post):
+        c = counts[b]
+        assert np.array_equal(out["prior_idx"][b, :c], m["prior_idx"]), b
+        assert np.array_equal(out["boxes"][b, :c], m["boxes"]), b
+        assert np.array_equal(out["patch_boxes"][b, :c], m["patch_boxes"]), b
+        assert np.array_equal(out["scores"][b, :c], m["scores"]), b
+        assert (out["prior_idx"][b, c:] == -1).all() and (out["boxes"][b, c:] == 0).all()
+
+
+def test_detect_small_golden(cuda_device, golden_dir):
+    g = np.load(os.path.join(golden_dir, "detect_small.npz"))
+    d = {k: g[k] for k in ("priors", "locations", "confidences", "restrictions", "max_to_keep", "offsets",
+                           "patch_dims", "image_dims", "is_flipped", "image_ids")}
+    out = _run(d)
+    assert np.array_equal(out["count"], g["out_count"])
+    rows = detect.detection_results({k: torch.from_numpy(v) for k, v in out.items()}, d["image_ids"])
+    assert np.array_equal(np.array([r["image_id"] for r in rows]), g["out_image_id"])
+    assert np.array_equal(np.array([r["bbox"] for r in rows]).reshape(-1, 4), g["out_bbox"])
+    assert np.array_equal(np.array([r["score"] for r in rows]), g["out_score"])
+    idx = np.concatenate([out["prior_idx"][b, :c] for b, c in enumerate(out["count"])])
+    assert np.array_equal(idx, g["out_prior_idx"])
+
+
+def test_detect_cfg3_head_golden(cuda_device, golden_dir):
+    g = np.load(os.path.join(golden_dir, "detect_cfg3_head.npz"))
+    cfg = dict(synth.DETECT_CONFIGS["cfg3"])
+    cfg.pop("nms_iou")
+    d = synth.make_detect_inputs(**cfg)
+    for k in ("locations", "confidences", "restrictions", "max_to_keep", "offsets", "patch_dims", "image_dims",
+              "is_flipped", "image_ids"):
+        d[k] = d[k][:16]
+    out = _run(d)
+    assert np.array_equal(out["count"], g["out_count"])
+    boxes = np.concatenate([out["boxes"][b, :c] for b, c in enumerate(out["count"])])
+    scores = np.concatenate([out["scores"][b, :c] for b, c in enumerate(out["count"])])
+    idx = np.concatenate([out["prior_idx"][b, :c] for b, c in enumerate(out["count"])])
+    assert np.array_equal(boxes, g["out_bbox"])
+    assert np.array_equal(scores.astype(np.float64), g["out_score"])
+    assert np.array_equal(idx, g["out_prior_idx"])
+
+
+@pytest.mark.parametrize("K,B,keep,patches,nms", [(5, 48, 200, False, None), (5, 48, 200, False, 0.5),
+                                                  (5, 40, 100, True, 0.5), (11, 24, 200, True, None),
+                                                  (11, 24, 200, True, 0.3), (7, 16, 50, True, 0.7)])
+def test_detect_vs_oracle(cuda_device, K, B, keep, patches, nms):
+    d = synth.make_detect_inputs(K=K, B=B, keep=keep, seed=400 + K + B, patches=patches)
+    d["confidences"][1, 5:300:3, 0] = d["confidences"][1, 5, 0]     # confidence ties
+    if patches:
+        d["restrictions"][3] = np.array([0.49, 0.49, 0.51, 0.51], np.float32)   # nothing survives
+    post = np_oracle.postprocess(d["locations"], d["confidences"], d["priors"], d["restrictions"],
+                                 d["max_to_keep"], d["offsets"], d["patch_dims"], d["image_dims"],
+                                 d["is_flipped"], nms_iou=nms)
+    for warps in (0, 4):
+        _compare(_run(d, nms_iou=nms, warps=warps), post)
+
+
+def test_detect_nms_heavy_overlap(cuda_device):
+    d = synth.make_detect_inputs(K=5, B=8, keep=200, seed=9)
+    d["locations"] *= 0.0                       # boxes == priors: dense, heavily overlapping grid
+    d["locations"] += np.random.default_rng(0).normal(0, 0.01, d["locations"].shape).astype(np.float32)
+    post = np_oracle.postprocess(d["locations"], d["confidences"], d["priors"], d["restrictions"],
+                                 d["max_to_keep"], d["offsets"], d["patch_dims"], d["image_dims"],
+                                 d["is_flipped"], nms_iou=0.5)
+    assert sum(m["boxes"].shape[0] for m in post) < 8 * 200     # NMS really suppresses here
+    _compare(_run(d, nms_iou=0.5), post)
+
+
+def test_detect_logits(cuda_device):
+    d = synth.make_detect_inputs(K=5, B=6, keep=100, seed=5)
+    out = _run(d, logits=True)
+    s = torch.sigmoid(torch.from_numpy(d["logits"])).numpy()
+    top = np.sort(s.reshape(6, -1), axis=1)[:, ::-1][:, :100]
+    np.testing.assert_allclose(out["scores"], top, rtol=2e-6)
+
+
+def test_filter_and_convert_single_image_mirrors(cuda_device):
+    d = synth.make_detect_inputs(K=5, B=4, keep=100, seed=6, patches=True)
+    boxes = np.clip(d["locations"][1] + d["priors"], 0., 1.)
+    fb0, fc0 = np_oracle.filter_proposals(boxes, d["confidences"][1], d["restrictions"][1])
+    fb, fc = detect.filter_proposals(dev(boxes), dev(d["confidences"][1]), d["restrictions"][1])
+    assert np.array_equal(fb.cpu().numpy(), fb0) and np.array_equal(fc.cpu().numpy(), fc0)
+    fb1, fc1 = detect.filter_proposals(dev(boxes), dev(d["confidences"][1]))        # default [.1,.1,.9,.9]
+    fb2, fc2 = np_oracle.filter_proposals(boxes, d["confidences"][1])
+    assert np.array_equal(fb1.cpu().numpy(), fb2) and np.array_equal(fc1.cpu().numpy(), fc2)
+    e, _ = detect.filter_proposals(dev(boxes), dev(d["confidences"][1]), [0.5, 0.5, 0.5, 0.5])
+    assert tuple(e.shape) == (0,)                                                   # reference: np.array([])
+    for flip in (0, 1):
+        c0 = np_oracle.convert_proposals(fb0, d["offsets"][1], d["patch_dims"][1], d["image_dims"][1], flip)
+        c1 = detect.convert_proposals(dev(fb0), d["offsets"][1], d["patch_dims"][1], d["image_dims"][1], flip)
+        assert c1.dtype == torch.float64 and np.array_equal(c1.cpu().numpy(), c0)
+
+
+def test_eval_topk_rows(cuda_device):
+    d = synth.make_detect_inputs(K=5, B=5, keep=100, seed=8)
+    rows0 = np_oracle.eval_topk(d["locations"], d["confidences"], d["priors"], 299, d["image_ids"], k=100)
+    rows1 = detect.eval_topk(dev(d["locations"]), dev(d["confidences"]), dev(d["priors"]), 299, d["image_ids"], k=100)
+    assert len(rows0) == len(rows1) == 500
+    assert np.array_equal(np.array(rows0, dtype=np.float64), np.array(rows1, dtype=np.float64))
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE configs[2] at full size (B=256): sortedness, bounds, idempotence."""
+    cfg = dict(synth.DETECT_CONFIGS["cfg3"])
+    nms = cfg.pop("nms_iou")
+    d = synth.make_detect_inputs(**cfg)
+    out = _run(d, nms_iou=nms)
+    assert (out["count"] <= 200).all() and (out["count"] > 0).all()
+    for b in range(0, 256, 17):
+        c = out["count"][b]
+        sc = out["scores"][b, :c]
+        assert (np.diff(sc) <= 0).all()
+        assert len(set(out["prior_idx"][b, :c].tolist())) == c
+        # kept set is NMS-stable: running NMS on the kept boxes keeps all of them
+        assert len(np_oracle.greedy_nms(out["patch_boxes"][b, :c], nms)) == c
+    out2 = _run(d, nms_iou=nms)
+    assert np.array_equal(out["prior_idx"], out2["prior_idx"])

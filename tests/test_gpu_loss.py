@@ -1,0 +1,125 @@
+"""-m gpu parity tests of the fused loss forward/backward (through the C ABI and
+the autograd mirror of reference loss.py:55) against the oracle.
+Tolerance (BASELINE.json north_star): losses, gradients within 1e-5 relative in
+fp32; matched indices bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from multibox_b200 import loss, synth
+from oracle import np_oracle
+from gpu_util import dev
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _run_gpu(d, alpha, logits=False, warps=0):
+    conf_in = d["logits"] if logits else d["confidences"]
+    out = loss.match_loss_raw(dev(d["locations"]), dev(conf_in).view(d["B"], d["P"]), dev(d["gt"]), dev(d["num_gt"]),
+                              dev(d["priors"]), alpha, flags=1 if logits else 0, want_mask=True, want_gt_idx=True,
+                              want_stacked=True, want_grads=True, want_conf_out=logits, warps=warps)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def _check(d, alpha, out, ref):
+    B, P = d["B"], d["P"]
+    assert out["results"][2] == 0
+    assert np.array_equal(out["mask"], ref["mask"])
+    assert np.array_equal(out["matched_gt_idx"], ref["matched_gt_idx"])
+    n = int(out["n_stacked"][0])
+    assert np.array_equal(out["stacked_gt"][:n], ref["stacked_gt"])
+    assert int(out["results"][3]) == int(ref["mask"].sum())
+    f64 = out["results"].view(np.float64)[2:4]
+    assert abs(f64[0] - ref["location_loss_f64"]) <= RTOL * abs(ref["location_loss_f64"]) + 1e-30
+    assert abs(f64[1] - ref["confidence_loss_f64"]) <= RTOL * abs(ref["confidence_loss_f64"])
+    np.testing.assert_allclose(out["results"][0], ref["location_loss"], rtol=RTOL)
+    np.testing.assert_allclose(out["results"][1], ref["confidence_loss"], rtol=RTOL)
+    np.testing.assert_allclose(out["d_locations"], ref["d_locations"], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(out["d_confidences"].reshape(B, P, 1), ref["d_confidences"], rtol=RTOL, atol=0)
+
+
+@pytest.mark.parametrize("name,alpha", [("cfg2", 1000.0), ("cfg2", 1.0)])
+def test_loss_cfg2(cuda_device, name, alpha):
+    cfg = dict(synth.TRAIN_CONFIGS[name])
+    cfg["alpha"] = alpha
+    d = synth.make_train_inputs(edge_cases=True, **cfg)
+    ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], alpha)
+    _check(d, alpha, _run_gpu(d, alpha), ref)
+
+
+@pytest.mark.parametrize("K,B,M,dist", [(7, 48, 100, "coco_person"), (11, 6, 200, "uniform")])
+def test_loss_other_shapes(cuda_device, K, B, M, dist):
+    d = synth.make_train_inputs(K=K, B=B, M=M, dist=dist, seed=31 + K, edge_cases=True)
+    ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], 1000.0)
+    for warps in (0, 1):
+        _check(d, 1000.0, _run_gpu(d, 1000.0, warps=warps), ref)
+
+
+def test_loss_from_logits(cuda_device):
+    d = synth.make_train_inputs(K=5, B=8, M=20, seed=55, edge_cases=True)
+    out = _run_gpu(d, 1000.0, logits=True)
+    s_gpu = out["confidences"].reshape(d["B"], d["P"], 1)
+    s_ref = torch.sigmoid(torch.from_numpy(d["logits"])).numpy()
+    np.testing.assert_allclose(s_gpu, s_ref, rtol=2e-6, atol=1e-37)
+    # feed the kernel's own sigmoid output to the oracle: everything downstream must agree
+    ref = np_oracle.add_loss(d["locations"], s_gpu, d["gt"], d["num_gt"], d["priors"], 1000.0)
+    assert np.array_equal(out["mask"], ref["mask"]) and np.array_equal(out["matched_gt_idx"], ref["matched_gt_idx"])
+    np.testing.assert_allclose(out["results"][:2], [ref["location_loss"], ref["confidence_loss"]], rtol=RTOL)
+    d_logits = ref["d_confidences"] * s_gpu * (np.float32(1.) - s_gpu)
+    np.testing.assert_allclose(out["d_confidences"].reshape(d["B"], d["P"], 1), d_logits, rtol=RTOL, atol=0)
+
+
+def test_autograd_mirror_of_add_loss(cuda_device):
+    d = synth.make_train_inputs(K=5, B=4, M=20, seed=12)
+    locs = dev(d["locations"]).requires_grad_(True)
+    confs = dev(d["confidences"]).requires_grad_(True)
+    ll, cl = loss.add_loss(locs, confs, dev(d["gt"]), dev(d["num_gt"]), dev(d["priors"]), 1000.0)
+    assert ll.shape == () and cl.shape == () and ll.dtype == torch.float32
+    (ll + 2.0 * cl).backward()
+    ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], 1000.0)
+    np.testing.assert_allclose(ll.item(), ref["location_loss"], rtol=RTOL)
+    np.testing.assert_allclose(cl.item(), ref["confidence_loss"], rtol=RTOL)
+    np.testing.assert_allclose(locs.grad.cpu().numpy(), ref["d_locations"], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(confs.grad.cpu().numpy(), 2.0 * ref["d_confidences"], rtol=RTOL, atol=0)
+
+
+def test_reference_test_properties(cuda_device):
+    """The five properties reference model_tests.py pins, on the CUDA path."""
+    rng = np.random.default_rng(0)
+    priors = rng.uniform(size=(646, 4)).astype(np.float32)          # model_tests.py:111
+    gt = np.zeros((2, 5, 4), np.float32)
+    gt[0, 0] = [0.1, 0.1, 0.9, 0.9]
+    locs = rng.normal(0, 0.1, size=(2, 646, 4)).astype(np.float32)
+    confs = rng.uniform(0.01, 0.99, size=(2, 646, 1)).astype(np.float32)
+
+    def run(sl, counts):
+        ll, cl = loss.add_loss(dev(locs[sl]), dev(confs[sl]), dev(gt[sl]), dev(np.array(counts, np.int32)),
+                               dev(priors), 1.0)
+        return ll.item(), cl.item()
+
+    ll, cl = run(slice(0, 1), [1])          # testSingleBoundingBox
+    assert ll > 0 and cl > 0
+    ll, cl = run(slice(0, 1), [0])          # testNoGTBoundingBox
+    assert ll == 0.0 and cl > 0
+    ll, cl = run(slice(0, 2), [1, 0])       # testBoxWithNoBox
+    assert ll > 0 and cl > 0
+
+
+def test_step_object_host_path(cuda_device):
+    d = synth.make_train_inputs(K=5, B=32, M=20, seed=1002)
+    step = loss.MultiboxLossStep(32, d["P"], 20, d["priors"], 1000.0)
+    ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], 1000.0)
+    for _ in range(3):      # workspace / output reuse across steps
+        ll, cl = step.step_host(d["locations"], d["confidences"], d["gt"], d["num_gt"])
+        np.testing.assert_allclose([ll, cl], [ref["location_loss"], ref["confidence_loss"]], rtol=RTOL)
+    np.testing.assert_allclose(step.out["d_locations"].cpu().numpy(), ref["d_locations"], rtol=RTOL, atol=0)
+
+
+def test_determinism(cuda_device):
+    d = synth.make_train_inputs(K=7, B=300, M=100, dist="coco_person", seed=2)
+    a = _run_gpu(d, 1000.0)
+    b = _run_gpu(d, 1000.0)
+    assert np.array_equal(a["results"].view(np.uint32), b["results"].view(np.uint32))
+    assert np.array_equal(a["d_confidences"].view(np.uint32), b["d_confidences"].view(np.uint32))

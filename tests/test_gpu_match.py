@@ -1,0 +1,194 @@
+"""-m gpu parity tests of the matching kernel (through the C ABI) against the
+oracle and the golden vectors generated from the reference's own code.
+Matched-prior indices, GT indices and stacked GT rows must be BIT-EXACT."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from multibox_b200 import loss, synth
+from oracle import c_oracle, np_oracle
+from gpu_util import boundary_inputs, dev, gpu_cost_matrix, gpu_nplog
+
+pytestmark = pytest.mark.gpu
+
+
+def _sha(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def _gpu_assign(loc, conf, gt, ng, B, alpha, warps=0):
+    if warps:
+        out = loss.match_loss_raw(dev(loc).view(B, -1, 4), dev(conf).view(B, -1), dev(gt), dev(ng), None, alpha,
+                                  flags=2, want_mask=True, want_gt_idx=True, want_stacked=True,
+                                  want_grads=False, warps=warps)
+        loss.raise_for_status(out["results"][2].item())
+        n = int(out["n_stacked"].item())
+        return out["mask"].cpu().numpy(), out["stacked_gt"][:n].cpu().numpy(), out["matched_gt_idx"].cpu().numpy()
+    m, s, g = loss.compute_assignments(dev(loc), dev(conf), dev(gt), dev(ng), B, alpha, return_indices=True)
+    return m.cpu().numpy(), s.cpu().numpy(), g.cpu().numpy()
+
+
+def test_native_library_is_loaded(cuda_device):
+    from multibox_b200 import _lib
+    lib = _lib.load()
+    assert lib.mbx_version() == 100
+    assert any("libmultibox_b200.so" in line for line in open("/proc/self/maps"))
+
+
+def test_nplog_bitwise_vs_numpy(cuda_device):
+    bits = np.arange(1, 0x7f800000, 251, dtype=np.uint32)
+    x = bits.view(np.float32)
+    assert np.array_equal(gpu_nplog(x).view(np.uint32), np.log(x).view(np.uint32))
+    with np.errstate(all="ignore"):
+        sp = np.array([0.0, np.inf, -1.0, np.nan, 1.0, 1e-10, 1e-45], dtype=np.float32)
+        a, b = gpu_nplog(sp), np.log(sp)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+
+
+def test_cost_matrix_bitwise_vs_numpy(cuda_device):
+    d = synth.make_train_inputs(K=5, B=3, M=20, seed=21, edge_cases=True)
+    loc, conf = boundary_inputs(d)
+    P = d["P"]
+    for b, alpha in ((1, 1000.0), (2, 1.0)):
+        sl = slice(b * P, (b + 1) * P)
+        gt = d["gt"][b][:max(1, d["num_gt"][b])]
+        lc, l1 = np_oracle.log_terms(conf[sl].copy())
+        Cn = np_oracle.cost_matrix(loc[sl], lc, l1, gt, np.float32(alpha))
+        Cg = gpu_cost_matrix(loc[sl], conf[sl], gt, alpha)
+        assert np.array_equal(Cn.view(np.uint64), Cg.view(np.uint64))
+
+
+def test_match_small_golden(cuda_device, golden_dir):
+    g = np.load(os.path.join(golden_dir, "match_small.npz"))
+    B = g["locations"].shape[0]
+    d = dict(B=B, locations=g["locations"], confidences=g["confidences"], priors=g["priors"])
+    loc, conf = boundary_inputs(d)
+    m, s, gi = _gpu_assign(loc, conf, g["gt"], g["num_gt"], B, float(g["alpha"]))
+    assert m.dtype == np.int32 and s.dtype == np.float32
+    assert np.array_equal(m, g["mask"])
+    assert np.array_equal(s, g["stacked_gt"])
+    assert np.array_equal(gi, g["matched_gt_idx"])
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_match_config_golden(cuda_device, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "match_%s.npz" % name))
+    d = synth.make_train_inputs(**synth.TRAIN_CONFIGS[name])
+    assert _sha(d["priors"], d["locations"], d["confidences"], d["gt"], d["num_gt"]) == str(g["inputs_sha256"])
+    loc, conf = boundary_inputs(d)
+    m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], d["B"], d["alpha"])
+    assert np.array_equal(np.nonzero(m)[0], g["matched_flat_idx"])
+    assert np.array_equal(gi[m == 1], g["matched_gt_idx"])
+    assert np.array_equal(s, g["stacked_gt"])
+
+
+@pytest.mark.parametrize("K,B,M,dist,alpha", [(5, 16, 20, "full", 1.0), (7, 24, 100, "coco_person", 1000.0),
+                                              (7, 8, 100, "full", 1000.0), (11, 8, 200, "uniform", 1000.0),
+                                              (11, 4, 200, "full", 10.0)])
+def test_match_vs_c_oracle(cuda_device, K, B, M, dist, alpha):
+    d = synth.make_train_inputs(K=K, B=B, M=M, dist=dist, seed=100 + K + M, alpha=alpha, edge_cases=True)
+    loc, conf = boundary_inputs(d)
+    m0, s0, g0 = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], B, alpha)
+    m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], B, alpha)
+    assert np.array_equal(m, m0)
+    assert np.array_equal(gi, g0)
+    assert np.array_equal(s, s0)
+
+
+@pytest.mark.parametrize("warps", [1, 2, 4, 8])
+def test_match_cta_sizes_agree(cuda_device, warps):
+    d = synth.make_train_inputs(K=5, B=12, M=20, dist="uniform", seed=77, edge_cases=True)
+    loc, conf = boundary_inputs(d)
+    m0, s0, g0 = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], 12, d["alpha"])
+    m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], 12, d["alpha"], warps=warps)
+    assert np.array_equal(m, m0) and np.array_equal(gi, g0) and np.array_equal(s, s0)
+
+
+def test_tie_rule_matches_scipy(cuda_device):
+    """Exact cost ties: scipy's scan order / tie rule decides; the kernel must
+    agree with scipy (via the C oracle that is pinned to scipy on tie-heavy inputs)."""
+    rng = np.random.default_rng(3)
+    P, M, B = 646, 20, 10
+    loc = np.zeros((B, P, 4), np.float32)
+    conf = np.full((B, P), 0.5, np.float32)
+    gt = np.zeros((B, M, 4), np.float32)
+    ng = np.zeros(B, np.int32)
+    for b in range(B):
+        n = int(rng.integers(1, M + 1))
+        ng[b] = n
+        gt[b, :n] = rng.integers(0, 3, size=(n, 4)).astype(np.float32) * 0.25      # duplicate GT rows
+        if b % 3 == 0:
+            loc[b] = 0.25                                                            # every prior identical
+        elif b % 3 == 1:
+            loc[b] = rng.integers(0, 3, size=(P, 4)).astype(np.float32) * 0.25      # heavy duplication
+            conf[b] = rng.choice([0.25, 0.5, 0.75], size=P).astype(np.float32)
+        else:
+            loc[b] = rng.integers(0, 2, size=(P, 1)).astype(np.float32) * 0.5
+    m0, s0, g0 = c_oracle.compute_assignments(loc.reshape(-1, 4), conf.reshape(-1), gt, ng, B, 8.0)
+    # the C oracle itself equals scipy on these (checked here once more, end to end)
+    m1, s1, g1 = np_oracle.compute_assignments(loc.reshape(-1, 4), conf.reshape(-1).copy(), gt, ng, np.int32(B),
+                                               np.float32(8.0), return_indices=True)
+    assert np.array_equal(m0, m1) and np.array_equal(g0, g1)
+    for warps in (0, 1, 8):
+        m, s, gi = _gpu_assign(loc.reshape(-1, 4), conf.reshape(-1), gt, ng, B, 8.0, warps=warps)
+        assert np.array_equal(m, m0), warps
+        assert np.array_equal(gi, g0), warps
+        assert np.array_equal(s, s0), warps
+
+
+def test_errors_like_scipy(cuda_device):
+    d = synth.make_train_inputs(K=5, B=2, M=20, dist="full", seed=5)
+    loc, conf = boundary_inputs(d)
+    bad = loc.copy()
+    bad[700, 2] = np.nan
+    with pytest.raises(ValueError, match="invalid numeric"):
+        loss.compute_assignments(dev(bad), dev(conf), dev(d["gt"]), dev(d["num_gt"]), 2, 1000.0)
+    with pytest.raises(ValueError):
+        np_oracle.compute_assignments(bad, conf.copy(), d["gt"], d["num_gt"], np.int32(2), np.float32(1000.0))
+    zero = np.zeros_like(conf)         # log(0) = -inf => every cost +inf => infeasible
+    with pytest.raises(ValueError, match="infeasible"):
+        loss.compute_assignments(dev(loc), dev(zero), dev(d["gt"]), dev(d["num_gt"]), 2, 1000.0)
+    # the workspace must be reusable after a failed batch
+    m, s = loss.compute_assignments(dev(loc), dev(conf), dev(d["gt"]), dev(d["num_gt"]), 2, 1000.0)
+    m0, s0, _ = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], 2, 1000.0)
+    assert np.array_equal(m.cpu().numpy(), m0) and np.array_equal(s.cpu().numpy(), s0)
+
+
+def test_empty_and_full_batches(cuda_device):
+    d = synth.make_train_inputs(K=5, B=4, M=20, dist="uniform", seed=8)
+    loc, conf = boundary_inputs(d)
+    ng = np.zeros(4, np.int32)
+    m, s = loss.compute_assignments(dev(loc), dev(conf), dev(d["gt"]), dev(ng), 4, 1000.0)
+    assert m.sum().item() == 0 and tuple(s.shape) == (0, 4)
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE configs[4]-shaped images (K=11, P=1420, M=200), 512 of them:
+    size-independent properties on all, exact comparison on a 24-image sample."""
+    d = synth.make_train_inputs(K=11, B=512, M=200, dist="uniform", seed=1005)
+    loc, conf = boundary_inputs(d)
+    B, P, M = 512, d["P"], 200
+    m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], B, 1000.0)
+    m2, gi2 = m.reshape(B, P), gi.reshape(B, P)
+    assert np.array_equal(m2.sum(1), d["num_gt"])                   # every GT matched exactly once
+    assert s.shape[0] == int(d["num_gt"].sum())
+    off = 0
+    for b in range(B):
+        n = int(d["num_gt"][b])
+        idx = gi2[b][m2[b] == 1]
+        assert np.array_equal(np.sort(idx), np.arange(n))           # a permutation of the GT rows
+        assert np.array_equal(s[off:off + n], d["gt"][b][idx])      # stacked rows in ascending prior order
+        off += n
+    assert (gi2[m2 == 0] == -1).all()
+    sample = np.arange(0, B, 22)[:24]
+    for b in sample:
+        sl = slice(b * P, (b + 1) * P)
+        m0, s0, g0 = c_oracle.compute_assignments(loc[sl], conf[sl], d["gt"][b:b + 1], d["num_gt"][b:b + 1], 1, 1000.0)
+        assert np.array_equal(m2[b], m0) and np.array_equal(gi2[b], g0)
