@@ -1,0 +1,528 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (contract: see the task description).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A "step" is one pass of the training hot path (GT->prior matching + multibox
+loss forward/backward) over one batch of synthetic head outputs.  The N=1
+workload is BASELINE.json configs[1]: Inception-ResNet-v2-shaped head outputs,
+5 aspect ratios (P=646 priors), batch 32, MAX_NUM_BBOXES=20.  With N>1 every rank
+runs the same per-GPU batch (weak scaling; images are independent) and the two
+loss scalars are SUM-all-reduced over NCCL every step.  Rank 0 prints ONE JSON line.
+A second object in the same line ("detect") reports BASELINE.json configs[2]
+(decode + top-k + NMS, batch 256) and "throughput_shape" reports a
+configs[4]-shaped per-GPU shard where the kernel is throughput- rather than
+launch-bound.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+L2_BYTES = 126 * 1024 * 1024
+
+
+# ----------------------------------------------------------------------------- helpers
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"       # /opt/skills/guides/B200_PROFILING.md
+
+
+def traffic_from_profiles(kernel):
+    """dram bytes per launch from the committed ncu summary, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def train_bytes_per_image(P, M, nbar):
+    """Algorithmic HBM bytes of match + loss fwd/bwd per image as this bench runs
+    it (minus the outputs the step does not request):
+    read offsets 16P + conf 4P + GT 16*n + count 4; write d_loc 16P + d_conf 4P +
+    per-image partials 20.  (mask / matched index / stacked GT are optional
+    outputs, not produced in the training step.)"""
+    return 40 * P + 16 * nbar + 24
+
+
+def detect_bytes_per_image(P, k):
+    """read offsets 16P + conf 4P + restriction 16 + keep 4 + conversion 28;
+    write k * (boxes f64 32 + patch boxes 16 + score 4 + idx 4) + count 4."""
+    return 20 * P + 56 * k + 52
+
+
+# ----------------------------------------------------------------------------- CPU legs (oracle)
+def _cpu_train_once(d):
+    from oracle import np_oracle
+    return np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], d["alpha"])
+
+
+_REF_D = None      # the batch, inherited by the forked workers (no per-step pickling)
+
+
+def _cpu_train_shard(args):
+    lo, hi = args
+    d = _REF_D
+    from oracle import np_oracle
+    out = np_oracle.add_loss(d["locations"][lo:hi], d["confidences"][lo:hi], d["gt"][lo:hi], d["num_gt"][lo:hi],
+                             d["priors"], d["alpha"])
+    return out["location_loss_f64"], out["confidence_loss_f64"]
+
+
+def cpu_baseline_train(d, budget_s=12.0):
+    """The oracle port (numpy/scipy restatement with the reference's loop
+    structure), one process / one core -- the way the reference executes this
+    path (under the GIL inside tf.py_func)."""
+    _cpu_train_once(d)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        _cpu_train_once(d)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 2000:
+            break
+    return {"value": d["B"] * n / el, "unit": "images/s", "cores": 1, "kind": "port",
+            "sample": "%d passes of the full %d-image batch (numpy/scipy oracle port, 1 process) in %.1f s"
+                      % (n, d["B"], el),
+            "host_cpus": os.cpu_count()}
+
+
+def cpu_baseline_train_c(d, budget_s=3.0):
+    """Extra, stronger CPU figure: the plain-C port of the matching (cost + LSAP),
+    single thread.  Matching only (it is >95% of the CPU path)."""
+    from oracle import c_oracle
+    B = d["B"]
+    loc = (d["locations"].reshape(-1, 4) + np.tile(d["priors"], (B, 1))).astype(np.float32)
+    conf = d["confidences"].reshape(-1) + np.float32(1e-10)
+    c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], B, d["alpha"])
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], B, d["alpha"])
+        n += 1
+    el = time.perf_counter() - t0
+    return {"value": B * n / el, "unit": "images/s", "cores": 1, "kind": "port",
+            "sample": "%d passes, plain-C matching port (oracle/c), 1 thread" % n}
+
+
+def cpu_baseline_detect(q, budget_s=6.0, nms=0.5):
+    from oracle import np_oracle
+    sub = 32
+    args = [q[k][:sub] for k in ("locations", "confidences")] + [q["priors"]] + \
+        [q[k][:sub] for k in ("restrictions", "max_to_keep", "offsets", "patch_dims", "image_dims", "is_flipped")]
+    n, t0 = 0, time.perf_counter()
+    while True:
+        np_oracle.postprocess(*args, nms_iou=nms)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s:
+            break
+    return {"value": sub * n / el, "unit": "images/s", "cores": 1, "kind": "port",
+            "sample": "%d passes over the first %d images of the batch (numpy oracle port)" % (n, sub)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (the
+    oracle port: numpy + scipy restatement with the reference's loops) on all
+    host cores, sharded by image across processes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    from multibox_b200 import synth
+    cfg = dict(synth.TRAIN_CONFIGS["cfg2"])
+    d = synth.make_train_inputs(**cfg)
+    B = d["B"]
+    cores = max(1, min(os.cpu_count() or 1, B))
+    try:
+        cores = min(cores, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    global _REF_D
+    _REF_D = d
+    bounds = [((B * i) // cores, (B * (i + 1)) // cores) for i in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(max(1, args.warmup)):
+            pool.map(_cpu_train_shard, bounds)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_train_shard, bounds)
+        el = time.perf_counter() - t0
+    value = B * args.steps / el
+    line = {
+        "impl": "reference", "metric": "match+loss images/sec", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": train_config_dict(d, args.gpus, cold="n/a (CPU)"),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": "each step = the full %d-image batch, sharded by image over %d processes; "
+                                   "numpy/scipy oracle port of reference loss.py:8-117" % (B, cores)},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def train_config_dict(d, n_gpus, cold):
+    return {"workload": "BASELINE configs[1]: Inception-ResNet-v2 299x299 multibox head outputs (random init), "
+                        "5 aspect ratios, P=%d priors, batch %d per GPU, MAX_NUM_BBOXES=%d: GT->prior matching + "
+                        "location/confidence loss fwd/bwd" % (d["P"], d["B"], d["M"]),
+            "K": d["K"], "P": d["P"], "batch_per_gpu": d["B"], "global_batch": d["B"] * n_gpus, "M": d["M"],
+            "alpha": d["alpha"], "mean_gt_per_image": float(d["num_gt"].mean()),
+            "parallelism": "image-sharded x%d" % n_gpus, "cache": cold}
+
+
+# ----------------------------------------------------------------------------- GPU legs
+def rotated_sets(t, nsets):
+    """nsets device copies of a batch tensor, images rolled by r: same distribution,
+    distinct addresses, so that consecutive steps never find their inputs in L2."""
+    import torch
+    return [torch.roll(t, shifts=r, dims=0).contiguous() if r else t.clone() for r in range(nsets)]
+
+
+def time_region(fn, steps, warmup, barrier):
+    """W untimed steps, then EXACTLY `steps` steps between barrier+synchronize on
+    both sides, timed with CUDA events on the launching (current) stream."""
+    import torch
+    for i in range(warmup):
+        fn(i)
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return e0.elapsed_time(e1) / 1e3
+
+
+def bench_train(d, steps, warmup, world, barrier, allreduce, want_e2e=True):
+    import torch
+    from multibox_b200 import loss
+    B, P, M = d["B"], d["P"], d["M"]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    per_set = 4 * (B * P * 4 + B * P + B * M * 4 + B)
+    nsets = max(2, min(1024, (2 * L2_BYTES) // per_set + 1))
+    t = {k: torch.from_numpy(np.ascontiguousarray(d[k])).to(dev) for k in ("locations", "confidences", "gt", "num_gt")}
+    locs = rotated_sets(t["locations"], nsets)
+    confs = rotated_sets(t["confidences"].view(B, P), nsets)
+    gts = rotated_sets(t["gt"], nsets)
+    ngs = rotated_sets(t["num_gt"], nsets)
+    step = loss.MultiboxLossStep(B, P, M, d["priors"], d["alpha"], device=dev)
+    loss64 = None
+
+    def one(i):
+        s = i % nsets
+        out = step.step(locs[s], confs[s], gts[s], ngs[s])
+        if world > 1:
+            allreduce(out["results"][4:8].view(torch.float64))
+
+    sec = time_region(one, steps, warmup, barrier)
+    # kernel-only duration of the dominant kernel, live, with events around each launch
+    kt = []
+    for i in range(min(steps, 50)):
+        s = (warmup + steps + i) % nsets
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step.step(locs[s], confs[s], gts[s], ngs[s])
+        b.record()
+        kt.append((a, b))
+    torch.cuda.synchronize()
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kt]))
+    res = {"sec": sec, "kernel_ms": kernel_ms, "nsets": nsets, "launches_per_step": 1}
+    if want_e2e:
+        hsets = 8      # pinned host sets (rolled), so the H2D source is not one hot buffer either
+        h = [{k: np.roll(d[k], r, axis=0) for k in ("locations", "confidences", "gt", "num_gt")} for r in range(hsets)]
+        pinned = []
+        for r in range(hsets):
+            pinned.append((torch.from_numpy(np.ascontiguousarray(h[r]["locations"])).pin_memory(),
+                           torch.from_numpy(np.ascontiguousarray(h[r]["confidences"].reshape(B, P))).pin_memory(),
+                           torch.from_numpy(np.ascontiguousarray(h[r]["gt"])).pin_memory(),
+                           torch.from_numpy(np.ascontiguousarray(h[r]["num_gt"])).pin_memory()))
+        last = {}
+
+        def e2e_step(i):
+            hl, hc, hg, hn = pinned[i % hsets]
+            step.h_loc, step.h_conf, step.h_gt, step.h_ng = hl, hc, hg, hn
+            last["v"] = step.step_pinned(validate=True)      # H2D x4, kernel, D2H of losses+status, sync
+            if world > 1:
+                allreduce(step.out["results"][4:8].view(torch.float64))
+
+        for i in range(warmup):
+            e2e_step(i)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            e2e_step(warmup + i)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        res.update(e2e_sec=el, h2d=step.h2d_bytes, d2h=step.d2h_bytes, last=last["v"])
+    return res
+
+
+def bench_detect(q, steps, warmup, barrier, nms_iou, want_e2e=True):
+    import torch
+    from multibox_b200 import detect
+    B, P, keep = q["B"], q["P"], q["keep"]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    per_set = 4 * (B * P * 5)
+    nsets = max(2, min(256, (2 * L2_BYTES) // per_set + 1))
+    names = ("locations", "confidences", "restrictions", "max_to_keep", "offsets", "patch_dims", "image_dims",
+             "is_flipped")
+    t = {k: torch.from_numpy(np.ascontiguousarray(q[k])).to(dev) for k in names}
+    pri = torch.from_numpy(q["priors"]).to(dev)
+    sets = {k: rotated_sets(t[k], nsets) for k in names}
+    out = {}
+
+    def one(i):
+        s = i % nsets
+        detect.postprocess(sets["locations"][s], sets["confidences"][s], pri, restrictions=sets["restrictions"][s],
+                           max_to_keep=sets["max_to_keep"][s], offsets=sets["offsets"][s],
+                           patch_dims=sets["patch_dims"][s], image_dims=sets["image_dims"][s],
+                           is_flipped=sets["is_flipped"][s], nms_iou=nms_iou, k_max=keep, out=out)
+
+    sec = time_region(one, steps, warmup, barrier)
+    kt = []
+    for i in range(min(steps, 50)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        one(warmup + steps + i)
+        b.record()
+        kt.append((a, b))
+    torch.cuda.synchronize()
+    res = {"sec": sec, "kernel_ms": float(np.mean([a.elapsed_time(b) for a, b in kt])), "nsets": nsets}
+    if want_e2e:
+        hp = {k: torch.from_numpy(np.ascontiguousarray(q[k])).pin_memory() for k in names}
+        dd = {k: torch.empty_like(t[k]) for k in names}
+        h_out = {"boxes": torch.empty((B, keep, 4), dtype=torch.float64).pin_memory(),
+                 "scores": torch.empty((B, keep), dtype=torch.float32).pin_memory(),
+                 "prior_idx": torch.empty((B, keep), dtype=torch.int32).pin_memory(),
+                 "count": torch.empty((B,), dtype=torch.int32).pin_memory()}
+        h2d = sum(hp[k].numel() * hp[k].element_size() for k in names)
+        d2h = sum(v.numel() * v.element_size() for v in h_out.values())
+
+        def e2e_step(i):
+            for k in names:
+                dd[k].copy_(hp[k], non_blocking=True)
+            detect.postprocess(dd["locations"], dd["confidences"], pri, restrictions=dd["restrictions"],
+                               max_to_keep=dd["max_to_keep"], offsets=dd["offsets"], patch_dims=dd["patch_dims"],
+                               image_dims=dd["image_dims"], is_flipped=dd["is_flipped"], nms_iou=nms_iou,
+                               k_max=keep, want_patch_boxes=False, out=out)
+            for k, v in h_out.items():
+                v.copy_(out[k], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for i in range(warmup):
+            e2e_step(i)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        res.update(e2e_sec=time.perf_counter() - t0, h2d=h2d, d2h=d2h)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the detect / throughput-shape / CPU legs")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from multibox_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+        def barrier():
+            dist.barrier()
+
+        def allreduce(t):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    else:
+        def barrier():
+            pass
+
+        def allreduce(t):
+            pass
+
+    peak, peak_kind = measured_peak()
+    cfg = dict(synth.TRAIN_CONFIGS["cfg2"])
+    cfg["seed"] = cfg["seed"] + 7919 * rank          # every rank owns different images
+    d = synth.make_train_inputs(**cfg)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    tr = bench_train(d, args.steps, args.warmup, world, barrier, allreduce)
+    clocks = sampler.stop() if rank == 0 else None
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sec = max_over_ranks(tr["sec"])
+    e2e_sec = max_over_ranks(tr["e2e_sec"])
+    kernel_ms = max_over_ranks(tr["kernel_ms"])
+    B, P, M = d["B"], d["P"], d["M"]
+    nbar = float(d["num_gt"].mean())
+    bytes_per_launch = train_bytes_per_image(P, M, nbar) * B
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    line = {
+        "metric": "match+loss images/sec", "value": world * B * args.steps / sec, "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": train_config_dict(d, world, cold="inputs rotate over %d device-resident sets (> 2x L2) so no step "
+                                                    "finds its inputs in L2" % tr["nsets"]),
+        "e2e": {"value": world * B * args.steps / e2e_sec, "unit": "images/s",
+                "h2d_bytes_per_step": tr["h2d"], "d2h_bytes_per_step": tr["d2h"],
+                "how": "MultiboxLossStep.step_pinned: 4 pinned H2D copies, 1 kernel, D2H of losses+status, "
+                       "stream sync, status check; wall clock"},
+        "gpu_launches": tr["launches_per_step"] * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "mbx_match_loss_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "peak_kind": "of " + peak_kind,
+                     "bytes_per_launch": bytes_per_launch, "kernel_ms": kernel_ms,
+                     "traffic": traffic_from_profiles("mbx_match_loss_kernel"),
+                     "note": "launch/latency-bound at this batch: %d CTAs on 148 SMs, %.2f MB per launch; the "
+                             "solver is bound by dependent shared-memory scans, not HBM (SURVEY.md 8d)"
+                             % (B, bytes_per_launch / 1e6)},
+        "clocks": clocks,
+    }
+    if world > 1:
+        dist.barrier()
+
+    if not args.no_extras:
+        # ---- secondary: detect path, BASELINE configs[2]
+        qcfg = dict(synth.DETECT_CONFIGS["cfg3"])
+        qcfg["seed"] += 7919 * rank
+        q = synth.make_detect_inputs(**qcfg)
+        dsteps = max(20, min(args.steps, 100))
+        dr = bench_detect(q, dsteps, args.warmup, barrier, q["nms_iou"])
+        dsec, dk, de2e = max_over_ranks(dr["sec"]), max_over_ranks(dr["kernel_ms"]), max_over_ranks(dr["e2e_sec"])
+        dbytes = detect_bytes_per_image(q["P"], q["keep"]) * q["B"]
+        dach = dbytes / (dk * 1e-3) / 1e9
+        line["detect"] = {
+            "metric": "decode+NMS images/sec", "value": world * q["B"] * dsteps / dsec, "unit": "images/s",
+            "steps": dsteps, "ms_per_step": 1e3 * dsec / dsteps,
+            "config": {"workload": "BASELINE configs[2]: sigmoid outputs -> decode + clip + filter + top-200 + "
+                                   "greedy NMS (IoU 0.5) + convert, batch %d per GPU, P=%d" % (q["B"], q["P"])},
+            "e2e": {"value": world * q["B"] * dsteps / de2e, "unit": "images/s",
+                    "h2d_bytes_per_step": dr["h2d"], "d2h_bytes_per_step": dr["d2h"]},
+            "roofline": {"bound": "hbm", "kernel": "mbx_detect_kernel", "achieved": dach, "peak": peak,
+                         "unit": "GB/s", "frac": dach / peak, "bytes_per_launch": dbytes, "kernel_ms": dk,
+                         "traffic": traffic_from_profiles("mbx_detect_kernel")},
+        }
+        # ---- a configs[4]-shaped per-GPU shard: where the kernel is throughput-bound
+        tcfg = dict(K=11, B=1024, M=200, dist="uniform", seed=1005 + 7919 * rank, alpha=1000.0)
+        td = synth.make_train_inputs(**tcfg)
+        tsteps = 10
+        tt = bench_train(td, tsteps, 3, 1, barrier, allreduce, want_e2e=False)
+        tsec, tk = max_over_ranks(tt["sec"]), max_over_ranks(tt["kernel_ms"])
+        tbytes = train_bytes_per_image(td["P"], 200, float(td["num_gt"].mean())) * 1024
+        tach = tbytes / (tk * 1e-3) / 1e9
+        evals = float((td["num_gt"].astype(np.float64) * td["P"]).sum())
+        line["throughput_shape"] = {
+            "workload": "BASELINE configs[4] shape: 11 aspect ratios (P=1420), MAX_NUM_BBOXES=200, 1024 images per GPU",
+            "value": world * 1024 * tsteps / tsec, "unit": "images/s", "ms_per_step": 1e3 * tsec / tsteps,
+            "min_cost_evals_per_s": world * evals * tsteps / tsec,
+            "roofline": {"bound": "hbm", "achieved": tach, "peak": peak, "unit": "GB/s", "frac": tach / peak,
+                         "kernel_ms": tk, "bytes_per_launch": tbytes,
+                         "note": "assignment solver: >= n*P cost evaluations per image (fp32 cost + fp64 duals), "
+                                 "compute/latency-bound, reported against the HBM figure as the contract asks"},
+        }
+        if rank == 0 and world == 1:
+            line["cpu_baseline"] = cpu_baseline_train(d)
+            line["cpu_baseline_c_port"] = cpu_baseline_train_c(d)
+            line["detect"]["cpu_baseline"] = cpu_baseline_detect(q)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -73,8 +73,9 @@ def convert_proposals(bboxes, offset, patch_dims, image_dims, is_flipped=0):
     fl = torch.as_tensor([1 if bool(int(torch.as_tensor(is_flipped).reshape(-1)[0])) else 0],
                          dtype=torch.int32).to(dev)
     out = torch.empty((1, K, 4), dtype=torch.float64, device=dev)
-    rc = lib.mbx_convert_proposals(_lib.ptr(b), _lib.ptr(i2(offset)), _lib.ptr(i2(patch_dims)),
-                                   _lib.ptr(i2(image_dims)), _lib.ptr(fl), None, 1, K, _lib.ptr(out), _stream(dev))
+    off, pd, imd = i2(offset), i2(patch_dims), i2(image_dims)   # keep alive until the launch is enqueued
+    rc = lib.mbx_convert_proposals(_lib.ptr(b), _lib.ptr(off), _lib.ptr(pd), _lib.ptr(imd), _lib.ptr(fl),
+                                   None, 1, K, _lib.ptr(out), _stream(dev))
     _lib.check(rc, "mbx_convert_proposals")
     return out[0]
 

@@ -1,0 +1,94 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), batch sharded by image.
+
+Every image is independent on this path, so the data
+path has no collective.  The only exchanges are
+  * one SUM all-reduce of the two loss scalars per training step (the
+    reference's losses are batch sums, loss.py:100-101, hence SUM not AVG);
+  * one all-gather of the padded detections (+ counts) per detect step;
+  * optionally an all-gather of the variable-length stacked GT rows, for callers
+    that want the global ``stacked_gt_bboxes`` of reference loss.py:53.
+Contiguous image blocks per rank keep batch order, so concatenating the rank
+outputs reproduces the single-GPU mask / stacked-GT / detection order.
+Works over NCCL (GPU) and gloo (CPU tensors; used by the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def is_dist():
+    return dist.is_available() and dist.is_initialized()
+
+
+def world():
+    return (dist.get_rank(), dist.get_world_size()) if is_dist() else (0, 1)
+
+
+def shard_range(batch_size, rank=None, world_size=None):
+    """Contiguous block [lo, hi) of images owned by `rank`; sizes differ by at most 1."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    base, rem = divmod(int(batch_size), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(tensors, batch_size, rank=None, world_size=None):
+    """Slices every tensor whose leading dimension is the batch."""
+    lo, hi = shard_range(batch_size, rank, world_size)
+    return {k: (v[lo:hi] if hasattr(v, "shape") and len(v.shape) > 0 and v.shape[0] == batch_size else v)
+            for k, v in tensors.items()}
+
+
+def allreduce_losses(losses, group=None, async_op=False):
+    """In-place SUM all-reduce of a small loss vector (e.g. the two float64
+    losses in results[4:8].view(float64)).  Returns the work handle if async."""
+    if not is_dist() or dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(losses, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def gather_detections(post, group=None):
+    """All-gathers the padded per-rank detection tensors (same B_local on every
+    rank) along the batch dimension; returns a dict of global tensors in batch order."""
+    if not is_dist() or dist.get_world_size(group) == 1:
+        return dict(post)
+    ws = dist.get_world_size(group)
+    out = {}
+    for k, t in post.items():
+        parts = [torch.empty_like(t) for _ in range(ws)]
+        dist.all_gather(parts, t.contiguous(), group=group)
+        out[k] = torch.cat(parts, dim=0)
+    return out
+
+
+def gather_stacked_gt(stacked_gt, group=None):
+    """All-gather of the variable-length [N_r,4] matched GT rows -> global [N,4]
+    in (rank, image, prior) = (image, prior) order."""
+    if not is_dist() or dist.get_world_size(group) == 1:
+        return stacked_gt
+    ws = dist.get_world_size(group)
+    n = torch.tensor([stacked_gt.shape[0]], dtype=torch.int64, device=stacked_gt.device)
+    counts = [torch.zeros_like(n) for _ in range(ws)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    padded = torch.zeros((cap, 4), dtype=stacked_gt.dtype, device=stacked_gt.device)
+    padded[:stacked_gt.shape[0]] = stacked_gt
+    parts = [torch.empty_like(padded) for _ in range(ws)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+def gather_variable_batch(t, batch_size, group=None):
+    """All-gather of per-rank tensors whose leading dim is that rank's shard of
+    `batch_size` images (shards may differ by one image)."""
+    if not is_dist() or dist.get_world_size(group) == 1:
+        return t
+    ws = dist.get_world_size(group)
+    sizes = [shard_range(batch_size, r, ws) for r in range(ws)]
+    cap = max(hi - lo for lo, hi in sizes)
+    padded = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    padded[:t.shape[0]] = t
+    parts = [torch.empty_like(padded) for _ in range(ws)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:hi - lo] for p, (lo, hi) in zip(parts, sizes)], dim=0)
