@@ -54,7 +54,11 @@ extern "C" {
 #define MBX_FLAG_BOUNDARY      2u   /* strict py_func boundary (reference loss.py:81): locations
                                        already have the prior added, confidences already have
                                        +1e-10 added; `priors` is ignored */
+#define MBX_FLAG_GENERIC       4u   /* force the generic shared-memory matching kernel (any P) instead
+                                       of the register-resident family (tuning / testing) */
 #define MBX_FLAG_WARPS_SHIFT   8    /* bits 8..15: force CTA size in warps (0 = heuristic) */
+#define MBX_FLAG_COLS_SHIFT    16   /* bits 16..23: force columns per thread of the register-resident
+                                       kernel (0 = heuristic) */
 
 int         mbx_version(void);
 const char *mbx_last_error(void);

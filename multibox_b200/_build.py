@@ -10,7 +10,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["mbx_api.cu", "mbx_match.cu", "mbx_detect.cu"]
+SOURCES = ["mbx_api.cu", "mbx_match.cu", "mbx_match_reg.cu", "mbx_detect.cu"]
 LIB = os.path.join(HERE, "libmultibox_b200.so")
 
 NVCC_FLAGS = [

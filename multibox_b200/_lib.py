@@ -18,7 +18,9 @@ _c_size_t = ctypes.c_size_t
 # flags / codes (mirror include/multibox_b200.h)
 FLAG_LOGITS = 1
 FLAG_BOUNDARY = 2
+FLAG_GENERIC = 4
 FLAG_WARPS_SHIFT = 8
+FLAG_COLS_SHIFT = 16
 STATUS_INVALID_COST = 1
 STATUS_INFEASIBLE = 2
 STATUS_BAD_NUM_GT = 4

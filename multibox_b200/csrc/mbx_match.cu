@@ -28,29 +28,9 @@
 // Every thread owns the columns j = tid, tid+T, ... so all per-column traffic is
 // conflict-free and needs no barrier; one __syncthreads per Dijkstra step
 // (the block-wide arg-min) and three per augmentation.
-#include <math_constants.h>
-
-#include "mbx_common.cuh"
+#include "mbx_match.cuh"
 
 namespace mbx {
-
-struct MatchParams {
-    const float *locations, *confidences, *gt, *priors;
-    const int32_t *num_gt;
-    int B, P, M;
-    float alpha;
-    unsigned flags;
-    int32_t *mask, *gt_idx;
-    float *stacked;
-    int32_t *n_stacked;
-    float *d_loc, *d_conf, *conf_out, *results;
-    // workspace
-    double *partials;        // [B][2]
-    int32_t *img_matched;    // [B]
-    int32_t *stk_offsets;    // [B+1] exclusive scan of num_gt
-    unsigned *ticket;        // [1]
-    unsigned *status;        // [1]
-};
 
 constexpr int kTieBit = 1 << 30;
 constexpr int kNoCol = kTieBit - 1;
@@ -81,21 +61,6 @@ __device__ __forceinline__ Cand warp_cand_min(Cand c) {
     return c;
 }
 
-// fp32 cost of (prior box, gt box) in the reference's numpy operation order
-// (loss.py:35): (alpha/2) * (sqrt(((d0^2+d1^2)+d2^2)+d3^2))**2 - log_c + log_1mc
-__device__ __forceinline__ float cost32(float4 l, float4 g, float half_alpha, float lc, float l1) {
-    float d0 = __fsub_rn(l.x, g.x), d1 = __fsub_rn(l.y, g.y), d2 = __fsub_rn(l.z, g.z), d3 = __fsub_rn(l.w, g.w);
-    float s = __fmul_rn(d0, d0);
-    s = __fadd_rn(s, __fmul_rn(d1, d1));
-    s = __fadd_rn(s, __fmul_rn(d2, d2));
-    s = __fadd_rn(s, __fmul_rn(d3, d3));
-    float nrm = __fsqrt_rn(s);
-    float c = __fmul_rn(half_alpha, __fmul_rn(nrm, nrm));
-    c = __fsub_rn(c, lc);
-    c = __fadd_rn(c, l1);
-    return c;
-}
-
 struct Smem {
     float4 *priors, *loc, *gt;
     double *spc, *v, *u, *red;
@@ -107,8 +72,6 @@ struct Smem {
     unsigned char *sc;
     uint64_t *bar;
 };
-
-__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Shared-memory carve-up; identical on host (size query) and device.
 __host__ __device__ inline size_t carve(Smem *s, unsigned char *base, int P, int M, int nwarps, bool has_priors) {
@@ -164,17 +127,6 @@ __host__ __device__ inline size_t carve(Smem *s, unsigned char *base, int P, int
         s->sc = base + o_sc;
     }
     return align_up(o, 16);
-}
-
-// Position of column j in scipy's `remaining` list after the first R removals of
-// the current augmentation (list filled in reverse, removal = swap with last).
-__device__ __forceinline__ int replay_pos(int j, int R, int P, const int *rm_idx) {
-    int pos = P - 1 - j, nrem = P;
-    for (int k = 0; k < R; ++k) {
-        --nrem;
-        if (pos == nrem) pos = rm_idx[k];
-    }
-    return pos;
 }
 
 // exclusive scan of clamp(num_gt, 0, M) -> offsets[B+1]; one CTA of 1024 threads.
@@ -593,6 +545,8 @@ static int launch_match(const MatchParams &p, size_t smem, int grid, cudaStream_
 template <int NWARPS>
 static int occupancy(size_t smem) {
     int nb = 0;
+    cudaFuncSetAttribute(mbx_match_loss_kernel<NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(smem));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mbx_match_loss_kernel<NWARPS>, NWARPS * 32, smem);
     return nb;
 }
@@ -709,6 +663,17 @@ extern "C" int mbx_match_loss(const float *locations, const float *confidences, 
     p.status = reinterpret_cast<unsigned *>(ws + wl.status);
 
     int nwarps = static_cast<int>((flags >> MBX_FLAG_WARPS_SHIFT) & 0xffu);
+    const int ncols = static_cast<int>((flags >> MBX_FLAG_COLS_SHIFT) & 0xffu);
+    if (stacked_gt || n_stacked) {
+        mbx_scan_num_gt_kernel<<<1, 1024, 0, st>>>(num_gt, B, M, p.stk_offsets, n_stacked);
+        if (int e = check_cuda(cudaGetLastError(), "launch mbx_scan_num_gt_kernel")) return e;
+    }
+    if (!(flags & MBX_FLAG_GENERIC)) {
+        // register-resident family first; it declines shapes it has no instantiation for
+        const int rc = launch_match_reg(p, nwarps, ncols, st);
+        if (rc != MBX_E_TOO_LARGE) return rc;
+        if (nwarps > 8) nwarps = 8;
+    }
     if (nwarps == 0) nwarps = P <= 256 ? 2 : (P <= 1024 ? 4 : 8);
     if (nwarps != 1 && nwarps != 2 && nwarps != 4 && nwarps != 8) {
         set_error("mbx_match_loss: forced warps must be 1, 2, 4 or 8");
@@ -719,10 +684,6 @@ extern "C" int mbx_match_loss(const float *locations, const float *confidences, 
         set_error("mbx_match_loss: P=%d M=%d needs %zu bytes of shared memory per CTA (max %d)", P, M, smem,
                   max_smem_optin());
         return MBX_E_TOO_LARGE;
-    }
-    if (stacked_gt || n_stacked) {
-        mbx_scan_num_gt_kernel<<<1, 1024, 0, st>>>(num_gt, B, M, p.stk_offsets, n_stacked);
-        if (int e = check_cuda(cudaGetLastError(), "launch mbx_scan_num_gt_kernel")) return e;
     }
     int occ = 1;
     switch (nwarps) {

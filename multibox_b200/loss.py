@@ -56,7 +56,7 @@ def raise_for_status(status):
 
 def match_loss_raw(locations, confidences, gt_bboxes, num_gt, priors, alpha, flags=0,
                    want_mask=False, want_gt_idx=False, want_stacked=False, want_grads=True,
-                   want_conf_out=False, warps=0, out=None):
+                   want_conf_out=False, warps=0, cols=0, out=None):
     """Thin wrapper of ``mbx_match_loss`` (see include/multibox_b200.h).  Inputs
     must already be contiguous fp32/int32 CUDA tensors; locations [B,P,4],
     confidences [B,P].  Returns a dict of device tensors; nothing synchronises.
@@ -86,7 +86,7 @@ def match_loss_raw(locations, confidences, gt_bboxes, num_gt, priors, alpha, fla
     results = buf("results", True, (8,), torch.float32)
     nbytes = lib.mbx_match_workspace_bytes(B, P, M)
     ws = _workspace(dev, nbytes)
-    flags = int(flags) | (int(warps) << _lib.FLAG_WARPS_SHIFT)
+    flags = int(flags) | (int(warps) << _lib.FLAG_WARPS_SHIFT) | (int(cols) << _lib.FLAG_COLS_SHIFT)
     rc = lib.mbx_match_loss(
         _lib.ptr(locations), _lib.ptr(confidences), _lib.ptr(gt_bboxes), _lib.ptr(num_gt), _lib.ptr(priors),
         B, P, M, float(alpha), flags,
@@ -219,6 +219,35 @@ class MultiboxLossStep:
                               self.alpha, flags=self.flags, want_mask=self.want_mask,
                               want_gt_idx=self.want_mask, want_stacked=self.want_stacked,
                               want_grads=True, warps=self.warps, out=self.out)
+
+    def prepare(self, locations, confidences, gt, num_gt):
+        """Returns a zero-argument callable that launches the step on these (fixed)
+        device tensors with all ctypes arguments pre-marshalled: the launch costs a
+        single foreign call (for latency-critical loops and CUDA-graph capture)."""
+        import ctypes
+        lib = _lib.load()
+        out = self.step(locations, confidences, gt, num_gt)     # allocates outputs / workspace once
+        B, P, M = self.B, self.P, self.M
+        ws = _workspace(self.device, lib.mbx_match_workspace_bytes(B, P, M))
+        flags = int(self.flags) | (int(self.warps) << _lib.FLAG_WARPS_SHIFT)
+        keep = (locations, confidences, gt, num_gt, ws, out)    # keep the tensors alive
+        c = ctypes
+        args = (c.c_void_p(locations.data_ptr()), c.c_void_p(confidences.data_ptr()), c.c_void_p(gt.data_ptr()),
+                c.c_void_p(num_gt.data_ptr()), c.c_void_p(self.priors.data_ptr()), B, P, M,
+                c.c_float(self.alpha), c.c_uint(flags),
+                c.c_void_p(_lib.ptr(out.get("mask"))), c.c_void_p(_lib.ptr(out.get("matched_gt_idx"))),
+                c.c_void_p(_lib.ptr(out.get("stacked_gt"))), c.c_void_p(_lib.ptr(out.get("n_stacked"))),
+                c.c_void_p(out["d_locations"].data_ptr()), c.c_void_p(out["d_confidences"].data_ptr()),
+                c.c_void_p(None), c.c_void_p(out["results"].data_ptr()), c.c_void_p(ws.data_ptr()),
+                c.c_size_t(ws.numel()))
+        fn = lib.mbx_match_loss
+        dev = self.device
+
+        def launch(_keep=keep):
+            rc = fn(*args, c.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            if rc:
+                _lib.check(rc, "mbx_match_loss")
+        return launch
 
     def step_host(self, locations, confidences, gt, num_gt, validate=True):
         """numpy in -> (location_loss, confidence_loss) python floats out; the

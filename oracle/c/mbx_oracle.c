@@ -68,6 +68,15 @@ void orc_nplogf_array(const float *in, float *out, int64_t n)
 }
 
 /* ---- rectangular LSAP (Crouse / scipy) ---------------------------------- */
+/* instrumentation: Dijkstra steps (full column scans) and column visits since the last reset */
+static int64_t g_scan_steps = 0, g_col_visits = 0;
+void orc_counters(int64_t *steps, int64_t *visits, int reset)
+{
+    if (steps) *steps = g_scan_steps;
+    if (visits) *visits = g_col_visits;
+    if (reset) { g_scan_steps = 0; g_col_visits = 0; }
+}
+
 /* cost is row-major [nr, nc] with nr <= nc (caller transposes tall inputs).
  * col4row[nr] receives the column assigned to each row. */
 static int lsap_wide(int64_t nr, int64_t nc, const double *cost, int64_t *col4row)
@@ -92,6 +101,7 @@ static int lsap_wide(int64_t nr, int64_t nc, const double *cost, int64_t *col4ro
             int64_t index = -1;
             double lowest = INFINITY;
             SR[i] = 1;
+            g_scan_steps++; g_col_visits += num_remaining;
             for (int64_t it = 0; it < num_remaining; it++) {
                 int64_t j = remaining[it];
                 double r = min_val + cost[i * nc + j] - u[i] - v[j];

@@ -14,10 +14,11 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 
 
-def _run_gpu(d, alpha, logits=False, warps=0):
+def _run_gpu(d, alpha, logits=False, warps=0, generic=False):
     conf_in = d["logits"] if logits else d["confidences"]
     out = loss.match_loss_raw(dev(d["locations"]), dev(conf_in).view(d["B"], d["P"]), dev(d["gt"]), dev(d["num_gt"]),
-                              dev(d["priors"]), alpha, flags=1 if logits else 0, want_mask=True, want_gt_idx=True,
+                              dev(d["priors"]), alpha, flags=(1 if logits else 0) | (4 if generic else 0),
+                              want_mask=True, want_gt_idx=True,
                               want_stacked=True, want_grads=True, want_conf_out=logits, warps=warps)
     torch.cuda.synchronize()
     return {k: v.cpu().numpy() for k, v in out.items()}
@@ -53,13 +54,16 @@ def test_loss_cfg2(cuda_device, name, alpha):
 def test_loss_other_shapes(cuda_device, K, B, M, dist):
     d = synth.make_train_inputs(K=K, B=B, M=M, dist=dist, seed=31 + K, edge_cases=True)
     ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], 1000.0)
-    for warps in (0, 1):
-        _check(d, 1000.0, _run_gpu(d, 1000.0, warps=warps), ref)
+    for warps, generic in ((0, False), (16, False), (0, True), (1, True)):
+        _check(d, 1000.0, _run_gpu(d, 1000.0, warps=warps, generic=generic), ref)
 
 
 def test_loss_from_logits(cuda_device):
     d = synth.make_train_inputs(K=5, B=8, M=20, seed=55, edge_cases=True)
     out = _run_gpu(d, 1000.0, logits=True)
+    out_g = _run_gpu(d, 1000.0, logits=True, generic=True)
+    for k in ("results", "d_confidences", "d_locations", "mask", "confidences"):
+        assert np.array_equal(out[k].view(np.uint32), out_g[k].view(np.uint32)), k      # both kernels, same bits
     s_gpu = out["confidences"].reshape(d["B"], d["P"], 1)
     s_ref = torch.sigmoid(torch.from_numpy(d["logits"])).numpy()
     np.testing.assert_allclose(s_gpu, s_ref, rtol=2e-6, atol=1e-37)

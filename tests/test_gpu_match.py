@@ -22,11 +22,11 @@ def _sha(*arrays):
     return h.hexdigest()
 
 
-def _gpu_assign(loc, conf, gt, ng, B, alpha, warps=0):
-    if warps:
+def _gpu_assign(loc, conf, gt, ng, B, alpha, warps=0, cols=0, generic=False):
+    if warps or cols or generic:
         out = loss.match_loss_raw(dev(loc).view(B, -1, 4), dev(conf).view(B, -1), dev(gt), dev(ng), None, alpha,
-                                  flags=2, want_mask=True, want_gt_idx=True, want_stacked=True,
-                                  want_grads=False, warps=warps)
+                                  flags=2 | (4 if generic else 0), want_mask=True, want_gt_idx=True,
+                                  want_stacked=True, want_grads=False, warps=warps, cols=cols)
         loss.raise_for_status(out["results"][2].item())
         n = int(out["n_stacked"].item())
         return out["mask"].cpu().numpy(), out["stacked_gt"][:n].cpu().numpy(), out["matched_gt_idx"].cpu().numpy()
@@ -102,12 +102,35 @@ def test_match_vs_c_oracle(cuda_device, K, B, M, dist, alpha):
     assert np.array_equal(s, s0)
 
 
-@pytest.mark.parametrize("warps", [1, 2, 4, 8])
-def test_match_cta_sizes_agree(cuda_device, warps):
+# (warps, cols, generic): the generic shared-memory kernel and the register-resident family
+VARIANTS = [(1, 0, True), (2, 0, True), (4, 0, True), (8, 0, True),
+            (4, 6, False), (4, 8, False), (8, 3, False), (8, 0, False), (16, 2, False), (16, 0, False),
+            (2, 0, False)]        # (2, 0): 11 columns per thread -> no instantiation -> generic fallback
+
+
+@pytest.mark.parametrize("warps,cols,generic", VARIANTS)
+def test_match_kernel_variants_agree(cuda_device, warps, cols, generic):
     d = synth.make_train_inputs(K=5, B=12, M=20, dist="uniform", seed=77, edge_cases=True)
     loc, conf = boundary_inputs(d)
     m0, s0, g0 = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], 12, d["alpha"])
-    m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], 12, d["alpha"], warps=warps)
+    m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], 12, d["alpha"], warps=warps, cols=cols, generic=generic)
+    assert np.array_equal(m, m0) and np.array_equal(gi, g0) and np.array_equal(s, s0)
+
+
+@pytest.mark.parametrize("P,M,warps", [(33, 5, 0), (33, 5, 1), (96, 30, 1), (200, 64, 0), (1024, 8, 0), (2500, 40, 0),
+                                       (4500, 16, 0)])
+def test_match_odd_shapes(cuda_device, P, M, warps):
+    """Prior counts that are not 129K+1 (single-warp CTAs, partially filled last column, P too
+    large for the register family -> generic kernel)."""
+    rng = np.random.default_rng(P)
+    B = 6
+    loc = rng.uniform(0, 1, size=(B * P, 4)).astype(np.float32)
+    conf = rng.uniform(0.01, 0.99, size=B * P).astype(np.float32)
+    ng = rng.integers(0, M + 1, size=B).astype(np.int32)
+    ng[0] = M
+    gt = synth.gt_boxes(rng, ng, M)
+    m0, s0, g0 = c_oracle.compute_assignments(loc, conf, gt, ng, B, 100.0)
+    m, s, gi = _gpu_assign(loc, conf, gt, ng, B, 100.0, warps=warps)
     assert np.array_equal(m, m0) and np.array_equal(gi, g0) and np.array_equal(s, s0)
 
 
@@ -136,11 +159,12 @@ def test_tie_rule_matches_scipy(cuda_device):
     m1, s1, g1 = np_oracle.compute_assignments(loc.reshape(-1, 4), conf.reshape(-1).copy(), gt, ng, np.int32(B),
                                                np.float32(8.0), return_indices=True)
     assert np.array_equal(m0, m1) and np.array_equal(g0, g1)
-    for warps in (0, 1, 8):
-        m, s, gi = _gpu_assign(loc.reshape(-1, 4), conf.reshape(-1), gt, ng, B, 8.0, warps=warps)
-        assert np.array_equal(m, m0), warps
-        assert np.array_equal(gi, g0), warps
-        assert np.array_equal(s, s0), warps
+    for warps, cols, generic in [(0, 0, False)] + VARIANTS:
+        m, s, gi = _gpu_assign(loc.reshape(-1, 4), conf.reshape(-1), gt, ng, B, 8.0, warps=warps, cols=cols,
+                               generic=generic)
+        assert np.array_equal(m, m0), (warps, cols, generic)
+        assert np.array_equal(gi, g0), (warps, cols, generic)
+        assert np.array_equal(s, s0), (warps, cols, generic)
 
 
 def test_errors_like_scipy(cuda_device):
@@ -159,6 +183,15 @@ def test_errors_like_scipy(cuda_device):
     m, s = loss.compute_assignments(dev(loc), dev(conf), dev(d["gt"]), dev(d["num_gt"]), 2, 1000.0)
     m0, s0, _ = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], 2, 1000.0)
     assert np.array_equal(m.cpu().numpy(), m0) and np.array_equal(s.cpu().numpy(), s0)
+
+
+def test_too_many_priors_is_an_argument_error(cuda_device):
+    from multibox_b200 import _lib
+    P, B = 70000, 1          # beyond both kernel families: reported, never silently mis-solved
+    with pytest.raises(_lib.MultiboxLibraryError, match="shared memory"):
+        loss.compute_assignments(torch.zeros(B * P, 4, device="cuda"), torch.full((B * P,), 0.5, device="cuda"),
+                                 torch.zeros(B, 2, 4, device="cuda"), torch.ones(B, dtype=torch.int32, device="cuda"),
+                                 B, 1.0)
 
 
 def test_empty_and_full_batches(cuda_device):
