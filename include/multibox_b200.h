@@ -181,6 +181,12 @@ int mbx_convert_proposals(const float *bboxes, const int32_t *offsets, const int
  * on float32, which reference loss.py:21,25 calls). */
 int mbx_debug_nplog(const float *in, float *out, long long n, void *stream);
 
+/* Adds to *mismatches (device uint64, caller-zeroed) the number of float32 bit patterns in
+ * [first_bits, first_bits+count) whose square root in the cost kernel differs from sqrt.rn
+ * (what numpy's np.linalg.norm / np.sqrt compute on the host). */
+int mbx_debug_sqrt_mismatches(unsigned first_bits, unsigned count, unsigned long long *mismatches,
+                              void *stream);
+
 /* The cost matrix of reference loss.py:33-35 for ONE image, as the matching
  * kernel evaluates it on the fly: loc [P,4] absolute boxes, conf [P] (epsilon
  * added), gt [n,4] -> C [P,n] float64 row-major. */

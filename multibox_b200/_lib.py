@@ -29,7 +29,7 @@ EXPORTS = ("mbx_version", "mbx_last_error", "mbx_device_info",
            "mbx_match_workspace_bytes", "mbx_match_loss",
            "mbx_detect_workspace_bytes", "mbx_detect",
            "mbx_filter_proposals", "mbx_convert_proposals",
-           "mbx_debug_nplog", "mbx_debug_cost_matrix")
+           "mbx_debug_nplog", "mbx_debug_cost_matrix", "mbx_debug_sqrt_mismatches")
 
 _lib = None
 
@@ -88,6 +88,8 @@ def load():
         _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]            # counts, B, K, out_boxes, stream
     lib.mbx_debug_nplog.restype = _c_int
     lib.mbx_debug_nplog.argtypes = [_c_void_p, _c_void_p, ctypes.c_longlong, _c_void_p]
+    lib.mbx_debug_sqrt_mismatches.restype = _c_int
+    lib.mbx_debug_sqrt_mismatches.argtypes = [_c_uint, _c_uint, _c_void_p, _c_void_p]
     lib.mbx_debug_cost_matrix.restype = _c_int
     lib.mbx_debug_cost_matrix.argtypes = [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_float,
                                           _c_void_p, _c_void_p]

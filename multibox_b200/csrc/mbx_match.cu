@@ -557,6 +557,17 @@ __global__ void mbx_debug_nplog_kernel(const float *in, float *out, long long n)
     for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) out[i] = nplogf(in[i]);
 }
 
+__global__ void mbx_debug_sqrt_kernel(unsigned first, unsigned count, unsigned long long *mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long k = blockIdx.x * 256ull + threadIdx.x; k < count; k += 256ull * gridDim.x) {
+        const float x = __uint_as_float(first + static_cast<unsigned>(k));
+        const float a = sqrt_rn_branchfree(x), b = __fsqrt_rn(x);
+        const bool same = (__float_as_uint(a) == __float_as_uint(b)) || (a != a && b != b);
+        bad += same ? 0 : 1;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 __global__ void mbx_debug_cost_kernel(const float *loc, const float *conf, const float *gt, int P, int n,
                                       float alpha, double *C) {
     const float half_alpha = __fdiv_rn(alpha, 2.0f);
@@ -584,6 +595,13 @@ extern "C" int mbx_debug_nplog(const float *in, float *out, long long n, void *s
     int grid = static_cast<int>(blocks < 148 * 16 ? blocks : 148 * 16);
     mbx_debug_nplog_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, n);
     return check_cuda(cudaGetLastError(), "launch mbx_debug_nplog_kernel");
+}
+
+extern "C" int mbx_debug_sqrt_mismatches(unsigned first_bits, unsigned count, unsigned long long *mismatches,
+                                         void *stream) {
+    if (!mismatches) return MBX_E_ARG;
+    mbx_debug_sqrt_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(first_bits, count, mismatches);
+    return check_cuda(cudaGetLastError(), "launch mbx_debug_sqrt_kernel");
 }
 
 extern "C" int mbx_debug_cost_matrix(const float *loc, const float *conf, const float *gt, int P, int n,

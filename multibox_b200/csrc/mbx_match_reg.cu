@@ -23,20 +23,37 @@
 // Shared memory per CTA: priors 16P + row4col 2P + O(M) -> ~13 KB at P=646.
 #include "mbx_match.cuh"
 
+// Optional phase timing (profiles/phase_timing.py builds with -DMBX_PHASE_TIMING): per-warp cycle
+// totals of the Dijkstra-step phases, written to the mask output buffer.  Compiled out otherwise.
+#ifdef MBX_PHASE_TIMING
+#define MBX_T(k)                                         \
+    do {                                                 \
+        const long long t_now__ = clock64();             \
+        t_acc[k] += t_now__ - t_last;                    \
+        t_last = t_now__;                                \
+    } while (0)
+#else
+#define MBX_T(k) \
+    do {         \
+    } while (0)
+#endif
+
 namespace mbx {
 
 namespace {
 
 constexpr unsigned kPayNone = 0xffffffffu;
-constexpr unsigned kPayTie = 1u << 15;
 
 struct RSmem {
     float4 *priors, *gt;
     double *u, *red;
     int4 *part;                 // [2][NWARPS] {key_hi, key_lo, payload, -}
     unsigned long long *pk;     // [NWARPS]
-    int *col4row, *rm_col, *rm_idx, *rm_pm, *visit, *ri;
+    int *col4row, *rm_col, *rm_idx, *rm_pm, *visit, *ri, *ctl;   // ctl[0] next general row, ctl[1] fast path off
+    uint2 *rowpart;             // [M][NWARPS] per-warp first-step minimum of each row {key32, column | tie<<31}
+    uint2 *rowmin;              // [M] block-wide first-step minimum of each row
     short *row4col;
+    unsigned char *dirty;       // [P] column dual is non-zero
     uint64_t *bar;
 };
 
@@ -52,6 +69,8 @@ __host__ __device__ inline size_t rcarve(RSmem *s, unsigned char *base, int P, i
     size_t o_pri = take(has_priors ? sizeof(float4) * P : 0, 16);
     size_t o_gt = take(sizeof(float4) * Mx, 16);
     size_t o_part = take(sizeof(int4) * 2 * nwarps, 16);
+    size_t o_rp = take(sizeof(uint2) * static_cast<size_t>(Mx) * nwarps, 8);
+    size_t o_rm = take(sizeof(uint2) * Mx, 8);
     size_t o_u = take(sizeof(double) * Mx, 8);
     size_t o_red = take(sizeof(double) * 3 * nwarps, 8);
     size_t o_pk = take(sizeof(unsigned long long) * nwarps, 8);
@@ -62,7 +81,9 @@ __host__ __device__ inline size_t rcarve(RSmem *s, unsigned char *base, int P, i
     size_t o_rmp = take(sizeof(int) * (M + 2), 4);
     size_t o_vis = take(sizeof(int) * (M + 2), 4);
     size_t o_ri = take(sizeof(int) * nwarps, 4);
+    size_t o_ctl = take(sizeof(int) * 4, 4);
     size_t o_r4c = take(sizeof(short) * P, 2);
+    size_t o_dirty = take(P, 1);
     if (s) {
         s->priors = reinterpret_cast<float4 *>(base + o_pri);
         s->gt = reinterpret_cast<float4 *>(base + o_gt);
@@ -78,6 +99,10 @@ __host__ __device__ inline size_t rcarve(RSmem *s, unsigned char *base, int P, i
         s->visit = reinterpret_cast<int *>(base + o_vis);
         s->ri = reinterpret_cast<int *>(base + o_ri);
         s->row4col = reinterpret_cast<short *>(base + o_r4c);
+        s->rowpart = reinterpret_cast<uint2 *>(base + o_rp);
+        s->rowmin = reinterpret_cast<uint2 *>(base + o_rm);
+        s->ctl = reinterpret_cast<int *>(base + o_ctl);
+        s->dirty = base + o_dirty;
     }
     return align_up(o, 16);
 }
@@ -92,6 +117,27 @@ __device__ __forceinline__ unsigned long long ord64(double x) {
 __device__ __forceinline__ double unord64(unsigned long long k) {
     const unsigned long long b = (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
     return __longlong_as_double(static_cast<long long>(b));
+}
+
+// order-preserving map float -> uint32 (-0.0 and +0.0 share one image)
+__device__ __forceinline__ unsigned ord32(float x) {
+    const unsigned b = __float_as_uint(__fadd_rn(x, 0.0f));
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float unord32(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+constexpr unsigned kColNone = 0x7fffffffu;
+constexpr unsigned kOrdInf32 = 0xff800000u;   // ord32(+inf)
+
+// lexicographic min of (key, col) over a warp; `tie` <=> two different columns share the minimal key
+__device__ __forceinline__ void warp_rowmin(unsigned &key, unsigned &col, bool &tie) {
+    const unsigned mk = __reduce_min_sync(0xffffffffu, key);
+    const bool mine = key == mk;
+    const unsigned mc = __reduce_min_sync(0xffffffffu, mine ? col : kColNone);
+    tie = __any_sync(0xffffffffu, mine && (tie || col != mc));
+    key = mk;
+    col = mc;
 }
 
 template <int NWARPS>
@@ -119,7 +165,7 @@ __device__ __forceinline__ void warp_argmin(unsigned &hi, unsigned &lo, unsigned
 }  // namespace
 
 template <int NWARPS, int C>
-__global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_reg_kernel(const MatchParams p) {
+__global__ void __launch_bounds__(NWARPS * 32, 1) mbx_match_loss_reg_kernel(const MatchParams p) {
     constexpr int T = NWARPS * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RSmem s;
@@ -146,6 +192,10 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_reg_kernel(const M
     }
     bool priors_ready = !has_priors;
     int pbuf = 0;
+#ifdef MBX_PHASE_TIMING
+    long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_last = clock64();
+#endif
 
     unsigned invalid_mask = 0;   // columns of this thread beyond P
 #pragma unroll
@@ -166,8 +216,11 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_reg_kernel(const M
         // ---- per-column state in registers
         float4 loc[C];
         float lc[C], l1[C], cf[C];
-        double v[C], spc[C];
-        int r4c[C], pm[C];
+        float c0[C];          // cost of the column against row `cur` (first Dijkstra step), fp32
+        double v[C];          // column dual
+        double spc64[C];      // shortest path cost when it is not simply (double)c0[c] (bit in `dbl`)
+        int pm[C], arow[C];   // visit index of the row that set spc64 (bit in `updm`); row at removal
+        unsigned vnz = 0u;    // which of this thread's columns have a non-zero dual
         const float4 *gl = reinterpret_cast<const float4 *>(p.locations) + row0;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -182,6 +235,11 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_reg_kernel(const M
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = tid + c * T;
+            v[c] = 0.0;
+            spc64[c] = INF;
+            c0[c] = CUDART_INF_F;
+            pm[c] = 0;
+            arow[c] = -1;
             if (j < P) {
                 if (has_priors) {
                     const float4 q = s.priors[j];
@@ -195,17 +253,17 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_reg_kernel(const M
                     if (p.conf_out) p.conf_out[row0 + j] = cf[c];
                 }
                 s.row4col[j] = -1;
+                s.dirty[j] = 0;
+                const float ce = boundary ? cf[c] : __fadd_rn(cf[c], kEps32);   // loss.py:74
+                lc[c] = nplogf(ce);                                              // loss.py:21
+                float w = __fsub_rn(1.0f, ce);                                   // loss.py:22-24
+                if (w > 1.0f) w = 1.0f;
+                if (w <= 0.0f) w = kEps32;
+                l1[c] = nplogf(w);                                               // loss.py:25
+            } else {
+                lc[c] = -CUDART_INF_F;   // a column that does not exist costs +inf: never selected
+                l1[c] = 0.0f;
             }
-            const float ce = boundary ? cf[c] : __fadd_rn(cf[c], kEps32);   // loss.py:74
-            lc[c] = nplogf(ce);                                              // loss.py:21
-            float w = __fsub_rn(1.0f, ce);                                   // loss.py:22-24
-            if (w > 1.0f) w = 1.0f;
-            if (w <= 0.0f) w = kEps32;
-            l1[c] = nplogf(w);                                               // loss.py:25
-            v[c] = 0.0;
-            spc[c] = INF;
-            r4c[c] = -1;
-            pm[c] = 0;
         }
         const float4 *gg = reinterpret_cast<const float4 *>(p.gt) + static_cast<size_t>(b) * M;
         for (int i = tid; i < n; i += T) {
@@ -214,100 +272,218 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_reg_kernel(const M
             s.col4row[i] = -1;
         }
         block_sync<NWARPS>();
+        MBX_T(0);   // prologue (load, logs)
 
         // ---- one shortest augmenting path per GT row (rows = GT, columns = priors)
         bool failed = false;
-        for (int cur = 0; cur < n && !failed; ++cur) {
+        bool ok = true;   // every cost entry seen so far is neither NaN nor -inf
+
+        // ---- batched first Dijkstra step of EVERY row, assuming all column duals are zero.
+        // Row i's first step is argmin_j (C(i,j) - v[j]); v is zero until an augmenting path
+        // passes THROUGH a column, so all rows can be evaluated up front with no barrier and
+        // RB*C independent cost chains per thread.  fp32 keys are exact here (r == C).
+        {
+            constexpr int RB = (C <= 2) ? 4 : ((C <= 4) ? 3 : 2);
+            for (int i0 = 0; i0 < n; i0 += RB) {
+                float4 g[RB];
+                float best[RB];
+                unsigned bcol[RB], btie[RB];
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    g[r] = s.gt[(i0 + r < n) ? (i0 + r) : (n - 1)];
+                    best[r] = CUDART_INF_F;
+                    bcol[r] = kColNone;
+                    btie[r] = 0u;
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) {
+                        const float c32 = cost32(loc[c], g[r], half_alpha, lc[c], l1[c]);
+                        ok = ok && (c32 > -CUDART_INF_F);
+                        const bool lt = c32 < best[r];
+                        const unsigned eq = c32 == best[r] ? 1u : 0u;
+                        best[r] = lt ? c32 : best[r];
+                        bcol[r] = lt ? static_cast<unsigned>(tid + c * T) : bcol[r];
+                        btie[r] = lt ? 0u : (btie[r] | eq);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    unsigned key = (bcol[r] == kColNone) ? 0xffffffffu : ord32(best[r]);
+                    unsigned col = bcol[r];
+                    bool tieb = btie[r] != 0u;
+                    warp_rowmin(key, col, tieb);
+                    if (lane == 0 && i0 + r < n) {
+                        if (NWARPS > 1)
+                            s.rowpart[(i0 + r) * NWARPS + warp] = make_uint2(key, col | (tieb ? 0x80000000u : 0u));
+                        else
+                            s.rowmin[i0 + r] = make_uint2(key, col | (tieb ? 0x80000000u : 0u));
+                    }
+                }
+            }
+            if (tid == 0) s.ctl[1] = 0;
+            if (NWARPS > 1) {
+                __syncthreads();
+                for (int i = warp; i < n; i += NWARPS) {
+                    uint2 e = make_uint2(0xffffffffu, kColNone);
+                    if (lane < NWARPS) e = s.rowpart[i * NWARPS + lane];
+                    unsigned key = e.x, col = e.y & kColNone;
+                    bool tieb = (e.y >> 31) != 0u;
+                    warp_rowmin(key, col, tieb);
+                    if (lane == 0) s.rowmin[i] = make_uint2(key, col | (tieb ? 0x80000000u : 0u));
+                }
+            }
+            block_sync<NWARPS>();
+        }
+        MBX_T(1);   // batched first step
+
+        // ---- rows in order.  Thread 0 disposes of every row whose precomputed first step is
+        // decisive (unique minimum at a column whose dual is still zero and which is unassigned:
+        // that column is the sink, the path is the single edge, no dual changes besides
+        // u[row] = min).  A dual can only make its column MORE expensive (v <= 0, enforced below),
+        // so a zero-dual minimum stays the true minimum.  Any other row is solved by the whole CTA
+        // with the general shortest-augmenting-path search below.
+        int cur = 0;
+        for (;;) {
+            if (tid == 0) {
+                const bool fast_off = s.ctl[1] != 0;
+                while (cur < n && !fast_off) {
+                    const uint2 rm = s.rowmin[cur];
+                    const unsigned col = rm.y & kColNone;
+                    if ((rm.y >> 31) || rm.x >= kOrdInf32 || col == kColNone) break;   // tie / infeasible
+                    if (s.dirty[col] || s.row4col[col] >= 0) break;                    // dual set / conflict
+                    s.row4col[col] = static_cast<short>(cur);
+                    s.col4row[cur] = static_cast<int>(col);
+                    s.u[cur] = static_cast<double>(unord32(rm.x));
+                    ++cur;
+                }
+                s.ctl[0] = cur;
+            }
+            block_sync<NWARPS>();
+            cur = s.ctl[0];
+            MBX_T(2);   // sequential fast rows
+            if (cur >= n) break;
+            // assigned bits of this thread's columns (thread 0 assigned sinks on its own)
+            unsigned asg = 0u;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (!((invalid_mask >> c) & 1u) && s.row4col[tid + c * T] >= 0) asg |= 1u << c;
             int i = cur, R = 0;
             double min_val = 0.0, ui = 0.0;
             unsigned scmask = invalid_mask;   // columns already scanned (or non-existent)
+            unsigned dbl = 0u, updm = 0u;     // see spc64 / pm above
             for (;;) {
                 const float4 g = s.gt[i];
-                double best = INF;
-                unsigned bpay = kPayNone;
-                bool tie = false;
+                unsigned long long key;
+                unsigned bj = kPayNone, tie = 0u;
                 if (R == 0) {
+                    // First Dijkstra step: min_val = 0, u[cur] = 0, nothing scanned, so
+                    // r = (0 + C) - 0 - v = C - v.  Where v == 0 (every column that was never
+                    // passed through by an augmenting path) r is the fp32 cost itself, and fp32
+                    // order == fp64 order of the widened values: no fp64 work on this path.
+                    float best32 = CUDART_INF_F;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        if ((scmask >> c) & 1u) continue;
                         const float c32 = cost32(loc[c], g, half_alpha, lc[c], l1[c]);
-                        if (!(c32 > -CUDART_INF_F)) status |= MBX_STATUS_INVALID_COST;   // NaN or -inf
-                        const double r = __dsub_rn(static_cast<double>(c32), v[c]);     // (0 + C) - 0 - v
-                        const double sp = r < INF ? r : INF;
-                        spc[c] = sp;
-                        pm[c] = 0;
-                        const unsigned pay = (static_cast<unsigned>(tid + c * T) << 16) | static_cast<unsigned>(r4c[c] + 1);
-                        if (sp < best) {
-                            best = sp;
-                            bpay = pay;
-                            tie = false;
-                        } else if (sp == best) {
-                            tie = true;
+                        ok = ok && (c32 > -CUDART_INF_F);
+                        c0[c] = c32;
+                        const bool lt = c32 < best32;
+                        const unsigned eq = c32 == best32 ? 1u : 0u;
+                        best32 = lt ? c32 : best32;
+                        bj = lt ? ((static_cast<unsigned>(tid + c * T) << 1) | ((asg >> c) & 1u)) : bj;
+                        tie = lt ? 0u : (tie | eq);
+                    }
+                    double best = static_cast<double>(best32);
+                    if (vnz) {   // rare: redo the thread-local minimum in fp64 with the duals
+                        best = INF;
+                        bj = kPayNone;
+                        tie = 0u;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            double sp = static_cast<double>(c0[c]);
+                            if ((vnz >> c) & 1u) {
+                                sp = __dsub_rn(sp, v[c]);
+                                spc64[c] = sp;
+                                dbl |= 1u << c;
+                            }
+                            const bool lt = sp < best;
+                            const unsigned eq = sp == best ? 1u : 0u;
+                            best = lt ? sp : best;
+                            bj = lt ? ((static_cast<unsigned>(tid + c * T) << 1) | ((asg >> c) & 1u)) : bj;
+                            tie = lt ? 0u : (tie | eq);
                         }
                     }
+                    key = (bj == kPayNone) ? ~0ull : ord64(best);
                 } else {
+                    double best = INF;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        if ((scmask >> c) & 1u) continue;
                         const float c32 = cost32(loc[c], g, half_alpha, lc[c], l1[c]);
                         const double r =
                             __dsub_rn(__dsub_rn(__dadd_rn(min_val, static_cast<double>(c32)), ui), v[c]);
-                        if (r < spc[c]) {
-                            spc[c] = r;
+                        const bool live = !((scmask >> c) & 1u);
+                        const double old = ((dbl >> c) & 1u) ? spc64[c] : static_cast<double>(c0[c]);
+                        const bool upd = live && (r < old);
+                        if (upd) {
+                            spc64[c] = r;
                             pm[c] = R;
+                            dbl |= 1u << c;
+                            updm |= 1u << c;
                         }
-                        const double sp = spc[c];
-                        const unsigned pay = (static_cast<unsigned>(tid + c * T) << 16) | static_cast<unsigned>(r4c[c] + 1);
-                        if (sp < best) {
-                            best = sp;
-                            bpay = pay;
-                            tie = false;
-                        } else if (sp == best) {
-                            tie = true;
-                        }
+                        const double sp = live ? (upd ? r : old) : INF;
+                        const bool lt = sp < best;
+                        const unsigned eq = sp == best ? 1u : 0u;
+                        best = lt ? sp : best;
+                        bj = lt ? ((static_cast<unsigned>(tid + c * T) << 1) | ((asg >> c) & 1u)) : bj;
+                        tie = lt ? 0u : (tie | eq);
                     }
+                    key = (bj == kPayNone) ? ~0ull : ord64(best);
                 }
+                MBX_T(3);   // general scan
                 // ---- block-wide arg-min of (path cost, column); exact ties flagged
-                const unsigned long long key = (bpay == kPayNone) ? ~0ull : ord64(best);
                 unsigned hi = static_cast<unsigned>(key >> 32), lo = static_cast<unsigned>(key);
-                unsigned pay = bpay;
-                warp_argmin(hi, lo, pay, tie);
+                unsigned pay = bj;
+                bool tieb = tie != 0u;
+                warp_argmin(hi, lo, pay, tieb);
                 if (NWARPS > 1) {
                     if (lane == 0)
                         s.part[pbuf * NWARPS + warp] =
-                            make_int4(static_cast<int>(hi), static_cast<int>(lo), static_cast<int>(pay | (tie ? kPayTie : 0u)), 0);
+                            make_int4(static_cast<int>(hi), static_cast<int>(lo), static_cast<int>(pay), tieb ? 1 : 0);
                     __syncthreads();
                     int4 e = make_int4(-1, -1, -1, 0);
                     if (lane < NWARPS) e = s.part[pbuf * NWARPS + lane];
                     hi = static_cast<unsigned>(e.x);
                     lo = static_cast<unsigned>(e.y);
                     pay = static_cast<unsigned>(e.z);
-                    tie = (pay != kPayNone) && (pay & kPayTie);
-                    if (pay != kPayNone) pay &= ~kPayTie;
-                    warp_argmin(hi, lo, pay, tie);
+                    tieb = e.w != 0;
+                    warp_argmin(hi, lo, pay, tieb);
                     pbuf ^= 1;
                 }
+                MBX_T(4);   // block arg-min (stage 2)
                 const unsigned long long mkey = (static_cast<unsigned long long>(hi) << 32) | lo;
-                if (pay == kPayNone || mkey >= ord64(INF)) {   // infeasible (scipy raises ValueError)
+                if (pay == kPayNone || mkey >= 0xfff0000000000000ull) {   // min is +inf: infeasible (scipy raises)
                     status |= MBX_STATUS_INFEASIBLE;
                     failed = true;
                     break;
                 }
                 min_val = unord64(mkey);
-                int jstar = static_cast<int>(pay >> 16);
-                int r4c_star = static_cast<int>(pay & 0x7fffu) - 1;
-                if (tie) {
+                int jstar = static_cast<int>(pay >> 1);
+                bool is_sink = !(pay & 1u);   // an unassigned column ends the search
+                if (tieb) {
                     // scipy's rule among the columns AT the minimum: the LAST unassigned one in
                     // `remaining` order wins, else the FIRST assigned one (rare path).
                     unsigned long long k = ~0ull;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        if (((scmask >> c) & 1u) || !(spc[c] == min_val)) continue;
+                        const double sp = ((dbl >> c) & 1u) ? spc64[c] : static_cast<double>(c0[c]);
+                        if (((scmask >> c) & 1u) || !(sp == min_val)) continue;
                         const int j = tid + c * T;
                         const int pos = replay_pos(j, R, P, s.rm_idx);
-                        const unsigned k2 = (r4c[c] < 0) ? static_cast<unsigned>(P - 1 - pos) : static_cast<unsigned>(P + pos);
+                        const bool assigned = (asg >> c) & 1u;
+                        const unsigned k2 = assigned ? static_cast<unsigned>(P + pos) : static_cast<unsigned>(P - 1 - pos);
                         const unsigned long long kk = (static_cast<unsigned long long>(k2) << 32) |
-                                                      (static_cast<unsigned>(j) << 16) | static_cast<unsigned>(r4c[c] + 1);
+                                                      (static_cast<unsigned>(j) << 1) | (assigned ? 1u : 0u);
                         k = kk < k ? kk : k;
                     }
 #pragma unroll
@@ -323,16 +499,47 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_reg_kernel(const M
                         for (int w = 1; w < NWARPS; ++w) k = s.pk[w] < k ? s.pk[w] : k;
                         __syncthreads();
                     }
-                    jstar = static_cast<int>((k >> 16) & 0xffffu);
-                    r4c_star = static_cast<int>(k & 0x7fffu) - 1;
+                    jstar = static_cast<int>((k & 0xffffffffu) >> 1);
+                    is_sink = !(k & 1u);
                 }
-                // ---- remove jstar from the scan set; its owner logs it
                 const int cstar = jstar / T;
-                if (jstar - cstar * T == tid) {
+                const bool owner = (jstar - cstar * T) == tid;
+                if (is_sink) {
+                    if (owner) {
+                        // ---- the sink's owner augments along the path back to row `cur`.  Every log
+                        // entry it reads was written before an earlier barrier; the sink itself needs
+                        // no log entry (nothing is scanned after it).
+                        int pmv = 0;
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+                            if (c == cstar && ((updm >> c) & 1u)) pmv = pm[c];
+                        scmask |= 1u << cstar;
+                        asg |= 1u << cstar;
+                        s.u[cur] = min_val;          // u[cur] was 0: 0 + min_val
+                        int col = jstar, m = pmv;
+                        for (;;) {
+                            const int row = (m == 0) ? cur : s.visit[m];
+                            s.row4col[col] = static_cast<short>(row);
+                            s.col4row[row] = col;
+                            if (m == 0) break;
+                            col = s.rm_col[m - 1];
+                            m = s.rm_pm[m - 1];
+                        }
+                    }
+                    ++R;
+                    break;
+                }
+                // Row of the assigned column jstar.  No walk can be in flight here: the previous
+                // augmentation's walk finished before this step's barrier.
+                const int r4c_star = s.row4col[jstar];
+                if (owner) {   // remove jstar from the scan set and log it
                     int pmv = 0;
 #pragma unroll
                     for (int c = 0; c < C; ++c)
-                        if (c == cstar) pmv = pm[c];
+                        if (c == cstar) {
+                            pmv = ((updm >> c) & 1u) ? pm[c] : 0;
+                            arow[c] = r4c_star;
+                        }
                     scmask |= 1u << cstar;
                     s.rm_col[R] = jstar;
                     s.rm_idx[R] = replay_pos(jstar, R, P, s.rm_idx);
@@ -340,43 +547,40 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_reg_kernel(const M
                     s.visit[R + 1] = r4c_star;
                 }
                 ++R;
-                if (r4c_star < 0) break;   // jstar is the sink
                 i = r4c_star;
                 ui = s.u[i];
                 if (NWARPS == 1) __syncwarp();
             }
-            block_sync<NWARPS>();
             if (failed) break;
-            // ---- dual update: v (owner registers), u (shared)
+            MBX_T(5);   // selection, log, walk
+            // ---- dual update: v (owner registers), u of the visited rows (shared, distinct rows).
+            // Only columns scanned BEFORE the sink move (the sink's own delta is 0).
+            if (R > 1) {
+                const unsigned scanned = scmask & ~invalid_mask;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                if (((scmask & ~invalid_mask) >> c) & 1u) {
-                    const double delta = __dsub_rn(min_val, spc[c]);
-                    v[c] = __dsub_rn(v[c], delta);
-                    // every scanned column except the sink is assigned, and its row was visited
-                    if (r4c[c] >= 0) s.u[r4c[c]] = __dadd_rn(s.u[r4c[c]], delta);
-                }
-                spc[c] = INF;
-            }
-            if (tid == 0) {
-                s.u[cur] = __dadd_rn(s.u[cur], min_val);
-                // ---- augment along the path, from the sink back to row `cur`
-                int k = R - 1;
-                for (;;) {
-                    const int m = s.rm_pm[k];
-                    const int row = (m == 0) ? cur : s.visit[m];
-                    const int col = s.rm_col[k];
-                    s.row4col[col] = static_cast<short>(row);
-                    s.col4row[row] = col;
-                    if (m == 0) break;
-                    k = m - 1;
+                for (int c = 0; c < C; ++c) {
+                    if (((scanned >> c) & 1u) && arow[c] >= 0) {
+                        const double sp = ((dbl >> c) & 1u) ? spc64[c] : static_cast<double>(c0[c]);
+                        const double delta = __dsub_rn(min_val, sp);
+                        v[c] = __dsub_rn(v[c], delta);
+                        s.u[arow[c]] = __dadd_rn(s.u[arow[c]], delta);
+                        if (v[c] != 0.0) {
+                            vnz |= 1u << c;
+                            s.dirty[tid + c * T] = 1;
+                            // the precomputed first steps rely on v <= 0; fp rounding could in
+                            // principle break that by an ulp: then every later row goes general
+                            if (v[c] > 0.0) s.ctl[1] = 1;
+                        }
+                        arow[c] = -1;
+                    }
                 }
             }
-            block_sync<NWARPS>();
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-                if (!((invalid_mask >> c) & 1u)) r4c[c] = s.row4col[tid + c * T];
+            ++cur;
+            block_sync<NWARPS>();   // walk, duals and dirty marks visible to thread 0
         }
+        MBX_T(6);   // dual update
+        if (!ok) status |= MBX_STATUS_INVALID_COST;
+        block_sync<NWARPS>();   // the last walk's row4col / col4row are visible below
 
         // ---- epilogue: mask, matched GT index, loss terms, gradients
         double acc_sq = 0.0, acc_conf = 0.0;
@@ -385,7 +589,7 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_reg_kernel(const M
         for (int c = 0; c < C; ++c) {
             const int j = tid + c * T;
             if (j >= P) continue;
-            const int r = r4c[c];
+            const int r = s.row4col[j];
             if (p.mask) p.mask[row0 + j] = r >= 0 ? 1 : 0;
             if (p.gt_idx) p.gt_idx[row0 + j] = r;
             n_match += r >= 0;
@@ -452,6 +656,13 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_reg_kernel(const M
     }
 
     if (status) atomicOr(p.status, status);
+#ifdef MBX_PHASE_TIMING
+    MBX_T(7);   // epilogue
+    if (lane == 0 && p.mask) {
+        long long *dbg = reinterpret_cast<long long *>(p.mask) + (static_cast<size_t>(blockIdx.x) * NWARPS + warp) * 8;
+        for (int k = 0; k < 8; ++k) dbg[k] = t_acc[k];
+    }
+#endif
 
     // ---- last CTA to finish reduces the per-image partials in a fixed order
     __shared__ bool is_last;

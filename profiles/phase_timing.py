@@ -1,0 +1,49 @@
+"""Builds a -DMBX_PHASE_TIMING copy of the library into gpurun_out/ and prints the per-phase cycle
+totals of the register-resident matching kernel (GPU box).  python profiles/phase_timing.py [warps]"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from multibox_b200 import _build, _lib, synth  # noqa: E402
+
+out_dir = os.path.join(ROOT, "gpurun_out")
+os.makedirs(out_dir, exist_ok=True)
+so = os.path.join(out_dir, "libmbx_timing.so")
+cmd = [_build.nvcc_path()] + [f for f in _build.NVCC_FLAGS if f not in ("-Xptxas", "-v")] + \
+    ["-DMBX_PHASE_TIMING", "-o", so] + [os.path.join(_build.CSRC, s) for s in _build.SOURCES]
+subprocess.check_call(cmd)
+_build.LIB = so
+_build.needs_build = lambda: False
+lib = _lib.load()
+from multibox_b200 import loss  # noqa: E402
+
+warps = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+names = ["prologue", "batched 1st step", "sequential rows", "general scan", "general argmin", "select/log/walk", "(loop exit)", "epilogue"]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+for label, d in (("cfg2", synth.make_train_inputs(**synth.TRAIN_CONFIGS["cfg2"])),
+                 ("cfg2 full n=20", synth.make_train_inputs(K=5, B=32, M=20, dist="full", seed=5))):
+    B, P = d["B"], d["P"]
+    for w in ([warps] if warps else [4, 8, 16]):
+        out = {"mask": torch.zeros(max(B * P, B * 16 * 8 * 2 + 64), dtype=torch.int32, device="cuda")}
+        for _ in range(2):
+            loss.match_loss_raw(dev(d["locations"]), dev(d["confidences"]).view(B, P), dev(d["gt"]), dev(d["num_gt"]),
+                                dev(d["priors"]), d["alpha"], want_mask=True, warps=w, out=out)
+        torch.cuda.synchronize()
+        t = out["mask"].cpu().numpy().view(np.int64)[:B * w * 8].reshape(B, w, 8)
+        b = int(np.argmax(d["num_gt"]))      # grid == B here: block b solves image b
+        print("%s warps=%d: image %d (n=%d) per-warp mean cycles by phase" % (label, w, b, d["num_gt"][b]))
+        tot = t[b].mean(0)
+        for k, nm in enumerate(names):
+            print("   %-16s %9.0f  (%.0f per augmentation)" % (nm, tot[k], tot[k] / max(1, d["num_gt"][b])))
+        print("   total %.0f cycles; slowest warp %.0f" % (tot.sum(), t[b].sum(1).max()))

@@ -40,6 +40,15 @@ if which in ("big", "all"):
         step.step(*args)
     torch.cuda.synchronize()
 
+if which in ("lat148",):
+    d = synth.make_train_inputs(K=5, B=148, M=20, dist="full", seed=5)
+    step = loss.MultiboxLossStep(d["B"], d["P"], d["M"], d["priors"], d["alpha"], warps=8)
+    args = (dev(d["locations"]), dev(d["confidences"]).view(d["B"], d["P"]), dev(d["gt"]), dev(d["num_gt"]))
+    for _ in range(reps):
+        flush_l2()
+        step.step(*args)
+    torch.cuda.synchronize()
+
 if which in ("b4096",):
     d = synth.make_train_inputs(K=5, B=4096, M=20, seed=3)
     step = loss.MultiboxLossStep(d["B"], d["P"], d["M"], d["priors"], d["alpha"])

@@ -52,6 +52,19 @@ def test_nplog_bitwise_vs_numpy(cuda_device):
     assert np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
 
 
+def test_sqrt_is_correctly_rounded(cuda_device):
+    """The kernels' branch-free sqrt equals sqrt.rn on EVERY float32 bit pattern (4 x 2^30)."""
+    from multibox_b200 import _lib
+    lib = _lib.load()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for first in (0x00000000, 0x40000000, 0x80000000, 0xC0000000):
+        _lib.check(lib.mbx_debug_sqrt_mismatches(first, 0x40000000, bad.data_ptr(),
+                                                 torch.cuda.current_stream().cuda_stream), "sqrt check")
+    assert bad.item() == 0
+    x = np.array([0.0, 1e-45, 1e-38, 7.9e-31, 2.0, 3.4e38, np.inf], dtype=np.float32)
+    assert np.array_equal(np.sqrt(x), np.sqrt(x.astype(np.float64)).astype(np.float32))   # host sqrt is rn too
+
+
 def test_cost_matrix_bitwise_vs_numpy(cuda_device):
     d = synth.make_train_inputs(K=5, B=3, M=20, seed=21, edge_cases=True)
     loc, conf = boundary_inputs(d)
@@ -225,3 +238,17 @@ def test_full_size_properties(cuda_device):
         sl = slice(b * P, (b + 1) * P)
         m0, s0, g0 = c_oracle.compute_assignments(loc[sl], conf[sl], d["gt"][b:b + 1], d["num_gt"][b:b + 1], 1, 1000.0)
         assert np.array_equal(m2[b], m0) and np.array_equal(gi2[b], g0)
+
+
+@pytest.mark.parametrize("warps", [0, 4, 8, 16, 1])
+def test_large_batch_stress(cuda_device, warps):
+    """Many images per persistent CTA (B=4096, K=5): every image checked against the C oracle
+    (fast port), twice, to flush out intra-CTA races."""
+    d = synth.make_train_inputs(K=5, B=4096, M=20, dist="uniform", seed=99)
+    loc, conf = boundary_inputs(d)
+    m0, s0, g0 = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], 4096, d["alpha"])
+    for _ in range(2):
+        m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], 4096, d["alpha"], warps=warps)
+        assert np.array_equal(m, m0)
+        assert np.array_equal(gi, g0)
+        assert np.array_equal(s, s0)
