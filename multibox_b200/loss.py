@@ -184,35 +184,48 @@ def add_loss_from_logits(locations, logits, batched_bboxes, batched_num_bboxes, 
 
 class MultiboxLossStep:
     """Allocation-free training-step object: preallocated outputs, one kernel
-    launch per step, optional pinned-host staging for callers that hold HOST
-    buffers (the reference's tf.py_func boundary hands numpy arrays over).
+    launch per step, and a host-buffer path for callers that hold HOST arrays
+    (the reference's tf.py_func boundary hands numpy arrays over).
 
-    step(...)      device tensors in, device results out (no sync)
-    step_host(...) host numpy arrays in (H2D from pinned memory), losses+status out
-                   (D2H), i.e. the end-to-end path a host caller sees.
+    step(...)        device tensors in, device results out (no sync)
+    step_host(...)   host numpy arrays in -> losses out: ONE packed pinned H2D copy,
+                     one kernel, one 32-byte D2H read-back, optionally replayed as a
+                     CUDA graph (use_graph=True) so a step costs one graph launch.
+    Inputs are staged in a single contiguous buffer laid out as
+    [locations B*P*4 | confidences B*P | gt B*M*4 | num_gt B] (fp32 / int32).
     """
 
     def __init__(self, B, P, M, priors, alpha, device="cuda", logits=False, want_mask=False,
-                 want_stacked=False, warps=0):
+                 want_stacked=False, warps=0, use_graph=False):
         self.B, self.P, self.M, self.alpha = B, P, M, float(alpha)
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.flags = _lib.FLAG_LOGITS if logits else 0
         self.warps = warps
         self.priors = _f32c(torch.as_tensor(priors).to(self.device), "priors")
         self.want_mask, self.want_stacked = want_mask, want_stacked
         self.out = {}
-        # device staging + pinned host staging for step_host
-        self.d_loc_in = torch.empty((B, P, 4), dtype=torch.float32, device=self.device)
-        self.d_conf_in = torch.empty((B, P), dtype=torch.float32, device=self.device)
-        self.d_gt_in = torch.empty((B, M, 4), dtype=torch.float32, device=self.device)
-        self.d_ng_in = torch.empty((B,), dtype=torch.int32, device=self.device)
-        self.h_loc = torch.empty((B, P, 4), dtype=torch.float32).pin_memory()
-        self.h_conf = torch.empty((B, P), dtype=torch.float32).pin_memory()
-        self.h_gt = torch.empty((B, M, 4), dtype=torch.float32).pin_memory()
-        self.h_ng = torch.empty((B,), dtype=torch.int32).pin_memory()
+        # packed staging: one pinned host buffer, one device buffer, typed views into both
+        n_loc, n_conf, n_gt = B * P * 4, B * P, B * M * 4
+        self._sections = (0, n_loc, n_loc + n_conf, n_loc + n_conf + n_gt, n_loc + n_conf + n_gt + B)
+        words = self._sections[-1]
+        self.h_in = torch.empty((words,), dtype=torch.float32).pin_memory()
+        self.d_in = torch.empty((words,), dtype=torch.float32, device=self.device)
+        self.h_loc, self.h_conf, self.h_gt, self.h_ng = self._views(self.h_in)
+        self.d_loc_in, self.d_conf_in, self.d_gt_in, self.d_ng_in = self._views(self.d_in)
         self.h_res = torch.empty((8,), dtype=torch.float32).pin_memory()
-        self.h2d_bytes = 4 * (B * P * 4 + B * P + B * M * 4 + B)
+        self.h2d_bytes = 4 * words
         self.d2h_bytes = 32
+        self.use_graph = bool(use_graph)
+        self._graph = None
+        self._launch = None
+
+    def _views(self, buf):
+        o = self._sections
+        B, P, M = self.B, self.P, self.M
+        return (buf[o[0]:o[1]].view(B, P, 4), buf[o[1]:o[2]].view(B, P), buf[o[2]:o[3]].view(B, M, 4),
+                buf[o[3]:o[4]].view(torch.int32))
 
     def step(self, locations, confidences, gt, num_gt):
         return match_loss_raw(locations, confidences.view(self.B, self.P), gt, num_gt, self.priors,
@@ -224,14 +237,13 @@ class MultiboxLossStep:
         """Returns a zero-argument callable that launches the step on these (fixed)
         device tensors with all ctypes arguments pre-marshalled: the launch costs a
         single foreign call (for latency-critical loops and CUDA-graph capture)."""
-        import ctypes
+        import ctypes as c
         lib = _lib.load()
         out = self.step(locations, confidences, gt, num_gt)     # allocates outputs / workspace once
         B, P, M = self.B, self.P, self.M
         ws = _workspace(self.device, lib.mbx_match_workspace_bytes(B, P, M))
         flags = int(self.flags) | (int(self.warps) << _lib.FLAG_WARPS_SHIFT)
         keep = (locations, confidences, gt, num_gt, ws, out)    # keep the tensors alive
-        c = ctypes
         args = (c.c_void_p(locations.data_ptr()), c.c_void_p(confidences.data_ptr()), c.c_void_p(gt.data_ptr()),
                 c.c_void_p(num_gt.data_ptr()), c.c_void_p(self.priors.data_ptr()), B, P, M,
                 c.c_float(self.alpha), c.c_uint(flags),
@@ -249,6 +261,26 @@ class MultiboxLossStep:
                 _lib.check(rc, "mbx_match_loss")
         return launch
 
+    def _enqueue_host_step(self):
+        self.d_in.copy_(self.h_in, non_blocking=True)           # one H2D copy of the packed inputs
+        self._launch()                                           # one kernel
+        self.h_res.copy_(self.out["results"], non_blocking=True)  # losses + status (32 bytes)
+
+    def _ensure_ready(self):
+        if self._launch is None:
+            self._launch = self.prepare(self.d_loc_in, self.d_conf_in, self.d_gt_in, self.d_ng_in)
+            torch.cuda.current_stream(self.device).synchronize()
+        if self.use_graph and self._graph is None:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self._enqueue_host_step()                        # warm-up on the capture stream
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self._enqueue_host_step()
+            self._graph = g
+
     def step_host(self, locations, confidences, gt, num_gt, validate=True):
         """numpy in -> (location_loss, confidence_loss) python floats out; the
         gradients stay on the device in self.out (they feed the network's backward)."""
@@ -259,14 +291,25 @@ class MultiboxLossStep:
         np.copyto(self.h_ng.numpy(), num_gt)
         return self.step_pinned(validate)
 
-    def step_pinned(self, validate=True):
-        """Same as step_host when the caller already wrote into the pinned buffers."""
-        self.d_loc_in.copy_(self.h_loc, non_blocking=True)
-        self.d_conf_in.copy_(self.h_conf, non_blocking=True)
-        self.d_gt_in.copy_(self.h_gt, non_blocking=True)
-        self.d_ng_in.copy_(self.h_ng, non_blocking=True)
-        out = self.step(self.d_loc_in, self.d_conf_in, self.d_gt_in, self.d_ng_in)
-        self.h_res.copy_(out["results"], non_blocking=True)
+    def step_pinned(self, validate=True, pinned=None):
+        """Same as step_host when the caller already wrote into the pinned staging
+        buffer (`self.h_in`, or another packed pinned buffer passed as `pinned`)."""
+        self._ensure_ready()
+        if pinned is not None and pinned is not self.h_in:
+            if self.use_graph:
+                self.h_in.copy_(pinned)          # graphs are bound to h_in; keep semantics identical
+            else:
+                self.d_in.copy_(pinned, non_blocking=True)
+                self._launch()
+                self.h_res.copy_(self.out["results"], non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                if validate:
+                    raise_for_status(self.h_res[2].item())
+                return float(self.h_res[0]), float(self.h_res[1])
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._enqueue_host_step()
         torch.cuda.current_stream(self.device).synchronize()
         if validate:
             raise_for_status(self.h_res[2].item())

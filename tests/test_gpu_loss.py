@@ -111,14 +111,26 @@ def test_reference_test_properties(cuda_device):
     assert ll > 0 and cl > 0
 
 
-def test_step_object_host_path(cuda_device):
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_step_object_host_path(cuda_device, use_graph):
     d = synth.make_train_inputs(K=5, B=32, M=20, seed=1002)
-    step = loss.MultiboxLossStep(32, d["P"], 20, d["priors"], 1000.0)
+    step = loss.MultiboxLossStep(32, d["P"], 20, d["priors"], 1000.0, use_graph=use_graph)
     ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], 1000.0)
     for _ in range(3):      # workspace / output reuse across steps
         ll, cl = step.step_host(d["locations"], d["confidences"], d["gt"], d["num_gt"])
         np.testing.assert_allclose([ll, cl], [ref["location_loss"], ref["confidence_loss"]], rtol=RTOL)
     np.testing.assert_allclose(step.out["d_locations"].cpu().numpy(), ref["d_locations"], rtol=RTOL, atol=0)
+    # a second, different batch through the same object (graph replays must pick up new host data)
+    d2 = synth.make_train_inputs(K=5, B=32, M=20, seed=77)
+    ref2 = np_oracle.add_loss(d2["locations"], d2["confidences"], d2["gt"], d2["num_gt"], d2["priors"], 1000.0)
+    ll, cl = step.step_host(d2["locations"], d2["confidences"], d2["gt"], d2["num_gt"])
+    np.testing.assert_allclose([ll, cl], [ref2["location_loss"], ref2["confidence_loss"]], rtol=RTOL)
+    bad = d2["locations"].copy()
+    bad[3, 5, 1] = np.nan
+    with pytest.raises(ValueError):
+        step.step_host(bad, d2["confidences"], d2["gt"], d2["num_gt"])
+    ll, cl = step.step_host(d2["locations"], d2["confidences"], d2["gt"], d2["num_gt"])      # recovers
+    np.testing.assert_allclose([ll, cl], [ref2["location_loss"], ref2["confidence_loss"]], rtol=RTOL)
 
 
 def test_determinism(cuda_device):
