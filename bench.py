@@ -261,7 +261,7 @@ def time_region(fn, steps, warmup, barrier):
     return e0.elapsed_time(e1) / 1e3
 
 
-def bench_train(d, steps, warmup, world, barrier, allreduce, want_e2e=True):
+def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True):
     import torch
     from multibox_b200 import loss
     B, P, M = d["B"], d["P"], d["M"]
@@ -273,16 +273,16 @@ def bench_train(d, steps, warmup, world, barrier, allreduce, want_e2e=True):
     confs = rotated_sets(t["confidences"].view(B, P), nsets)
     gts = rotated_sets(t["gt"], nsets)
     ngs = rotated_sets(t["num_gt"], nsets)
-    step = loss.MultiboxLossStep(B, P, M, d["priors"], d["alpha"], device=dev)
+    step = loss.MultiboxLossStep(B, P, M, d["priors"], d["alpha"], device=dev, peer=peer)
     # one pre-marshalled launch closure per input set: a step is ONE foreign call + one kernel
     launches = [step.prepare(locs[s], confs[s], gts[s], ngs[s]) for s in range(nsets)]
-    res64 = step.out["results"][4:8].view(torch.float64)
     torch.cuda.synchronize()
+    barrier()
 
     def one(i):
+        # N > 1: the SUM all-reduce of the two loss scalars is fused into this kernel (peer
+        # memory over NVLink, mbx_match_loss_allreduce); no separate collective is launched
         launches[i % nsets]()
-        if world > 1:
-            allreduce(res64)
 
     sec = time_region(one, steps, warmup, barrier)
     # kernel-only duration of the dominant kernel, live, with events around each launch
@@ -302,7 +302,7 @@ def bench_train(d, steps, warmup, world, barrier, allreduce, want_e2e=True):
         hsets = 4
         hsteps = []
         for r in range(hsets):
-            hs = loss.MultiboxLossStep(B, P, M, d["priors"], d["alpha"], device=dev, use_graph=True)
+            hs = loss.MultiboxLossStep(B, P, M, d["priors"], d["alpha"], device=dev, use_graph=True, peer=peer)
             np.copyto(hs.h_loc.numpy(), np.roll(d["locations"], r, axis=0))
             np.copyto(hs.h_conf.numpy(), np.roll(d["confidences"].reshape(B, P), r, axis=0))
             np.copyto(hs.h_gt.numpy(), np.roll(d["gt"], r, axis=0))
@@ -312,9 +312,7 @@ def bench_train(d, steps, warmup, world, barrier, allreduce, want_e2e=True):
 
         def e2e_step(i):
             hs = hsteps[i % hsets]
-            last["v"] = hs.step_pinned(validate=True)     # graph: H2D, kernel, D2H; sync; status check
-            if world > 1:
-                allreduce(hs.out["results"][4:8].view(torch.float64))
+            last["v"] = hs.step_pinned(validate=True)     # graph: H2D, kernel (+fused all-reduce), D2H; sync
 
         for i in range(max(warmup, hsets)):
             e2e_step(i)
@@ -322,10 +320,11 @@ def bench_train(d, steps, warmup, world, barrier, allreduce, want_e2e=True):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(steps):
-            e2e_step(warmup + i)
+            e2e_step(max(warmup, hsets) + i)
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
-        res.update(e2e_sec=el, h2d=hsteps[0].h2d_bytes, d2h=hsteps[0].d2h_bytes, last=last["v"])
+        res.update(e2e_sec=el, h2d=hsteps[0].h2d_bytes, d2h=hsteps[0].d2h_bytes, last=last["v"],
+                   last_global=hsteps[(max(warmup, hsets) + steps - 1) % hsets].global_losses())
     return res
 
 
@@ -419,14 +418,13 @@ def main():
         def barrier():
             dist.barrier()
 
-        def allreduce(t):
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        from multibox_b200 import dist as mdist
+        peer = mdist.PeerAllreduce()
     else:
         def barrier():
             pass
 
-        def allreduce(t):
-            pass
+        peer = None
 
     peak, peak_kind = measured_peak()
     cfg = dict(synth.TRAIN_CONFIGS["cfg2"])
@@ -436,7 +434,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    tr = bench_train(d, args.steps, args.warmup, world, barrier, allreduce)
+    tr = bench_train(d, args.steps, args.warmup, world, barrier, peer)
     clocks = sampler.stop() if rank == 0 else None
 
     def max_over_ranks(x):
@@ -465,6 +463,9 @@ def main():
                        "copy + 1 kernel + D2H of losses/status, then stream sync and status check, every step; "
                        "wall clock"},
         "gpu_launches": tr["launches_per_step"] * args.steps,
+        "collective": ("loss SUM all-reduce fused into the kernel (NVLink peer stores + system-scope arrival "
+                       "counter), no NCCL call per step") if world > 1 else None,
+        "last_losses": {"local": tr.get("last"), "global": tr.get("last_global")},
         "roofline": {"bound": "hbm", "kernel": "mbx_match_loss_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "peak_kind": "of " + peak_kind,
                      "bytes_per_launch": bytes_per_launch, "kernel_ms": kernel_ms,
@@ -502,7 +503,7 @@ def main():
         tcfg = dict(K=11, B=1024, M=200, dist="uniform", seed=1005 + 7919 * rank, alpha=1000.0)
         td = synth.make_train_inputs(**tcfg)
         tsteps = 10
-        tt = bench_train(td, tsteps, 3, 1, barrier, allreduce, want_e2e=False)
+        tt = bench_train(td, tsteps, 3, world, barrier, peer, want_e2e=False)
         tsec, tk = max_over_ranks(tt["sec"]), max_over_ranks(tt["kernel_ms"])
         tbytes = train_bytes_per_image(td["P"], 200, float(td["num_gt"].mean())) * 1024
         tach = tbytes / (tk * 1e-3) / 1e9
@@ -528,5 +529,23 @@ def main():
     return 0
 
 
+def _guard_stdout():
+    """Rank 0 must print exactly ONE JSON line on stdout; libraries (NCCL prints its version
+    banner on stdout) must not.  Route fd 1 to stderr for the run and keep the real stdout
+    for the final line."""
+    real = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 if __name__ == "__main__":
+    _real_stdout = _guard_stdout()
+    _print = print
+
+    def print(*a, **k):      # noqa: A001  (the JSON line goes to the real stdout)
+        k.setdefault("file", _real_stdout)
+        _print(*a, **k)
+        _real_stdout.flush()
+
     sys.exit(main())

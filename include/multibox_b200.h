@@ -46,6 +46,9 @@ extern "C" {
 #define MBX_STATUS_INVALID_COST  1u  /* NaN or -inf cost entry (scipy: "matrix contains invalid numeric entries") */
 #define MBX_STATUS_INFEASIBLE    2u  /* no finite assignment (scipy: "cost matrix is infeasible") */
 #define MBX_STATUS_BAD_NUM_GT    4u  /* num_gt[b] outside [0, M] (clamped)      */
+#define MBX_STATUS_AR_TIMEOUT    8u  /* fused loss all-reduce: a peer rank never arrived */
+
+#define MBX_MAX_PEERS 8              /* GPUs of one NVLink/NVSwitch box */
 
 /* flags */
 #define MBX_FLAG_LOGITS        1u   /* `confidences` holds logits; the kernel applies the
@@ -96,10 +99,13 @@ size_t mbx_match_workspace_bytes(int B, int P, int M);
  *   d_locations     [B,P,4] dL/d locations
  *   d_confidences   [B,P]   dL/d confidences (d logits with MBX_FLAG_LOGITS)
  *   confidences_out [B,P]   sigmoid(logits) (MBX_FLAG_LOGITS only)
- *   results         [8]     float32: [0] location_loss, [1] confidence_loss,
+ *   results         [16]    float32 words: [0] location_loss, [1] confidence_loss,
  *                           [2] status word (exact small integer), [3] number of
  *                           matched priors (exact while < 2^24), [4..7] the two
- *                           losses as float64 (2 x 8 bytes)
+ *                           losses as float64 (2 x 8 bytes), [8..11] the two losses
+ *                           summed over all ranks as float64 (== [4..7] unless
+ *                           mbx_match_loss_allreduce is used with world > 1),
+ *                           [12],[13] the same as float32
  *   n_stacked       [1]     int32 number of rows written to stacked_gt
  * The status word is also OR-ed into results[2]; it is 0 when every image was
  * solved.  grads/loss outputs are produced iff `results` is non-NULL.
@@ -113,6 +119,30 @@ int mbx_match_loss(const float *locations, const float *confidences,
                    float *d_locations, float *d_confidences,
                    float *confidences_out, float *results,
                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* Same as mbx_match_loss, with the SUM all-reduce of the two loss scalars over the
+ * `world` GPUs of one NVLink box FUSED into the kernel (reference semantics: the losses
+ * are batch sums, loss.py:100-101; the batch is sharded by image, one process per GPU).
+ * The last CTA stores its sums into every rank's slot table through peer memory
+ * (NVLink P2P stores), signals arrival with a system-scope atomic, waits for the other
+ * ranks and adds the slots in rank order; results[8..13] then hold the global sums,
+ * bit-identical on every rank.  Every rank must call this once per step, in step order.
+ *   peer_buffers [world]  HOST array of device pointers: rank r's symmetric buffer of
+ *                         mbx_allreduce_buffer_bytes() bytes (zero-filled once), mapped
+ *                         into this process (CUDA IPC / VMM; torch symmetric memory)
+ * A rank that never arrives trips MBX_STATUS_AR_TIMEOUT (~2 s) instead of hanging. */
+size_t mbx_allreduce_buffer_bytes(void);
+int mbx_match_loss_allreduce(const float *locations, const float *confidences,
+                             const float *gt_bboxes, const int32_t *num_gt,
+                             const float *priors, int B, int P, int M, float alpha,
+                             unsigned flags,
+                             int32_t *mask, int32_t *matched_gt_idx,
+                             float *stacked_gt, int32_t *n_stacked,
+                             float *d_locations, float *d_confidences,
+                             float *confidences_out, float *results,
+                             void *workspace, size_t workspace_bytes,
+                             const unsigned long long *peer_buffers, int world, int rank,
+                             void *stream);
 
 /* ------------------------------------------------------------------------- *
  * Detection post-processing

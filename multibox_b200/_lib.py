@@ -24,9 +24,13 @@ FLAG_COLS_SHIFT = 16
 STATUS_INVALID_COST = 1
 STATUS_INFEASIBLE = 2
 STATUS_BAD_NUM_GT = 4
+STATUS_AR_TIMEOUT = 8
+MAX_PEERS = 8
+RESULT_WORDS = 16
 
 EXPORTS = ("mbx_version", "mbx_last_error", "mbx_device_info",
            "mbx_match_workspace_bytes", "mbx_match_loss",
+           "mbx_allreduce_buffer_bytes", "mbx_match_loss_allreduce",
            "mbx_detect_workspace_bytes", "mbx_detect",
            "mbx_filter_proposals", "mbx_convert_proposals",
            "mbx_debug_nplog", "mbx_debug_cost_matrix", "mbx_debug_sqrt_mismatches")
@@ -69,6 +73,10 @@ def load():
         _c_void_p, _c_void_p, _c_void_p, _c_void_p,                 # mask, matched_gt_idx, stacked_gt, n_stacked
         _c_void_p, _c_void_p, _c_void_p, _c_void_p,                 # d_loc, d_conf, conf_out, results
         _c_void_p, _c_size_t, _c_void_p]                            # workspace, bytes, stream
+    lib.mbx_allreduce_buffer_bytes.restype = _c_size_t
+    lib.mbx_allreduce_buffer_bytes.argtypes = []
+    lib.mbx_match_loss_allreduce.restype = _c_int
+    lib.mbx_match_loss_allreduce.argtypes = lib.mbx_match_loss.argtypes[:-1] + [_c_void_p, _c_int, _c_int, _c_void_p]
     lib.mbx_detect_workspace_bytes.restype = _c_size_t
     lib.mbx_detect_workspace_bytes.argtypes = [_c_int, _c_int, _c_int]
     lib.mbx_detect.restype = _c_int

@@ -493,21 +493,12 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_kernel(const Match
             C += s.red[NWARPS + w];
             Mt += s.pv[w];
         }
-        const double loc_loss = static_cast<double>(p.alpha) * (A / 2.0);   // loss.py:100
-        const unsigned st = atomicOr(p.status, 0u);
-        p.results[0] = static_cast<float>(loc_loss);
-        p.results[1] = static_cast<float>(C);
-        p.results[2] = static_cast<float>(st);
-        p.results[3] = static_cast<float>(Mt);
-        reinterpret_cast<double *>(p.results)[2] = loc_loss;
-        reinterpret_cast<double *>(p.results)[3] = C;
-        *p.ticket = 0u;    // workspace reusable by the next launch
-        *p.status = 0u;
+        finalize_losses(p, A, C, Mt);
     }
 }
 
 struct WsLayout {
-    size_t partials, img_matched, offsets, ticket, status, total;
+    size_t partials, img_matched, offsets, ticket, status, ar_seq, total;
 };
 static WsLayout ws_layout(int B) {
     WsLayout w;
@@ -516,6 +507,8 @@ static WsLayout ws_layout(int B) {
     o += 8;
     w.status = o;
     o += 8;
+    w.ar_seq = o;
+    o += 16;
     w.partials = o;
     o += sizeof(double) * 2 * static_cast<size_t>(B);
     w.img_matched = o;
@@ -623,6 +616,25 @@ extern "C" int mbx_match_loss(const float *locations, const float *confidences, 
                               int32_t *n_stacked, float *d_locations, float *d_confidences,
                               float *confidences_out, float *results, void *workspace, size_t workspace_bytes,
                               void *stream) {
+    return mbx_match_loss_allreduce(locations, confidences, gt_bboxes, num_gt, priors, B, P, M, alpha, flags, mask,
+                                    matched_gt_idx, stacked_gt, n_stacked, d_locations, d_confidences,
+                                    confidences_out, results, workspace, workspace_bytes, nullptr, 1, 0, stream);
+}
+
+extern "C" size_t mbx_allreduce_buffer_bytes(void) { return align_up(kArBytes, 256); }
+
+extern "C" int mbx_match_loss_allreduce(const float *locations, const float *confidences, const float *gt_bboxes,
+                                        const int32_t *num_gt, const float *priors, int B, int P, int M,
+                                        float alpha, unsigned flags, int32_t *mask, int32_t *matched_gt_idx,
+                                        float *stacked_gt, int32_t *n_stacked, float *d_locations,
+                                        float *d_confidences, float *confidences_out, float *results,
+                                        void *workspace, size_t workspace_bytes,
+                                        const unsigned long long *peer_buffers, int world, int rank,
+                                        void *stream) {
+    if (world < 1 || world > MBX_MAX_PEERS || rank < 0 || rank >= world || (world > 1 && !peer_buffers)) {
+        set_error("mbx_match_loss_allreduce: bad world=%d rank=%d (max %d ranks)", world, rank, MBX_MAX_PEERS);
+        return MBX_E_ARG;
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (B < 0 || P <= 0 || M < 0) {
         set_error("mbx_match_loss: bad sizes B=%d P=%d M=%d", B, P, M);
@@ -679,6 +691,10 @@ extern "C" int mbx_match_loss(const float *locations, const float *confidences, 
     p.stk_offsets = reinterpret_cast<int32_t *>(ws + wl.offsets);
     p.ticket = reinterpret_cast<unsigned *>(ws + wl.ticket);
     p.status = reinterpret_cast<unsigned *>(ws + wl.status);
+    p.ar_seq = reinterpret_cast<unsigned *>(ws + wl.ar_seq);
+    p.ar_world = world;
+    p.ar_rank = rank;
+    for (int r = 0; r < MBX_MAX_PEERS; ++r) p.ar_peer[r] = (world > 1 && r < world) ? peer_buffers[r] : 0ull;
 
     int nwarps = static_cast<int>((flags >> MBX_FLAG_WARPS_SHIFT) & 0xffu);
     const int ncols = static_cast<int>((flags >> MBX_FLAG_COLS_SHIFT) & 0xffu);

@@ -697,16 +697,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mbx_match_loss_reg_kernel(cons
             Cc += s.red[NWARPS + w];
             Mt += s.red[2 * NWARPS + w];
         }
-        const double loc_loss = static_cast<double>(p.alpha) * (A / 2.0);   // loss.py:100
-        const unsigned st = atomicOr(p.status, 0u);
-        p.results[0] = static_cast<float>(loc_loss);
-        p.results[1] = static_cast<float>(Cc);
-        p.results[2] = static_cast<float>(st);
-        p.results[3] = static_cast<float>(Mt);
-        reinterpret_cast<double *>(p.results)[2] = loc_loss;
-        reinterpret_cast<double *>(p.results)[3] = Cc;
-        *p.ticket = 0u;    // workspace reusable by the next launch
-        *p.status = 0u;
+        finalize_losses(p, A, Cc, Mt);
     }
 }
 

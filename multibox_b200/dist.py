@@ -92,3 +92,35 @@ def gather_variable_batch(t, batch_size, group=None):
     parts = [torch.empty_like(padded) for _ in range(ws)]
     dist.all_gather(parts, padded, group=group)
     return torch.cat([p[:hi - lo] for p, (lo, hi) in zip(parts, sizes)], dim=0)
+
+
+class PeerAllreduce:
+    """Peer-memory plumbing for the all-reduce that is FUSED into the matching/loss kernel
+    (mbx_match_loss_allreduce): one small symmetric buffer per rank, mapped into every
+    process of the NVLink box through torch's symmetric memory (CUDA VMM handles exchanged
+    over the process group).  PyTorch only allocates and maps; the exchange itself is plain
+    peer stores + a system-scope atomic inside the kernel's last CTA."""
+
+    def __init__(self, group=None, device=None):
+        import ctypes
+        from . import _lib
+        self.rank, self.world = world()
+        self.ptr_array = None
+        self._keep = None
+        if self.world == 1:
+            return
+        if self.world > _lib.MAX_PEERS:
+            raise ValueError("fused all-reduce supports up to %d ranks" % _lib.MAX_PEERS)
+        import torch.distributed._symmetric_memory as symm_mem
+        lib = _lib.load()
+        nbytes = int(lib.mbx_allreduce_buffer_bytes())
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, group=dist.group.WORLD if group is None else group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                      # every buffer is zeroed before anyone writes
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        assert len(ptrs) == self.world
+        self.ptr_array = (ctypes.c_ulonglong * self.world)(*ptrs)
+        self._keep = (buf, hdl)

@@ -52,15 +52,19 @@ def raise_for_status(status):
         raise ValueError("cost matrix is infeasible")
     if status & _lib.STATUS_BAD_NUM_GT:
         raise ValueError("num_gt_bboxes entry outside [0, MAX_NUM_BBOXES]")
+    if status & _lib.STATUS_AR_TIMEOUT:
+        raise RuntimeError("fused loss all-reduce timed out: a peer rank did not launch its step")
 
 
 def match_loss_raw(locations, confidences, gt_bboxes, num_gt, priors, alpha, flags=0,
                    want_mask=False, want_gt_idx=False, want_stacked=False, want_grads=True,
-                   want_conf_out=False, warps=0, cols=0, out=None):
+                   want_conf_out=False, warps=0, cols=0, out=None, peer=None):
     """Thin wrapper of ``mbx_match_loss`` (see include/multibox_b200.h).  Inputs
     must already be contiguous fp32/int32 CUDA tensors; locations [B,P,4],
     confidences [B,P].  Returns a dict of device tensors; nothing synchronises.
-    `out` may carry preallocated output tensors (same keys) to avoid allocation."""
+    `out` may carry preallocated output tensors (same keys) to avoid allocation.
+    `peer` (multibox_b200.dist.PeerAllreduce) fuses the cross-GPU SUM of the two
+    losses into the kernel; results[8:12].view(float64) then holds the global sums."""
     lib = _lib.load()
     B, P = locations.shape[0], locations.shape[1]
     M = gt_bboxes.shape[1]
@@ -83,16 +87,20 @@ def match_loss_raw(locations, confidences, gt_bboxes, num_gt, priors, alpha, fla
     d_loc = buf("d_locations", want_grads, (B, P, 4), torch.float32)
     d_conf = buf("d_confidences", want_grads, (B, P, 1), torch.float32)
     conf_out = buf("confidences", want_conf_out, (B, P, 1), torch.float32)
-    results = buf("results", True, (8,), torch.float32)
+    results = buf("results", True, (_lib.RESULT_WORDS,), torch.float32)
     nbytes = lib.mbx_match_workspace_bytes(B, P, M)
     ws = _workspace(dev, nbytes)
     flags = int(flags) | (int(warps) << _lib.FLAG_WARPS_SHIFT) | (int(cols) << _lib.FLAG_COLS_SHIFT)
-    rc = lib.mbx_match_loss(
-        _lib.ptr(locations), _lib.ptr(confidences), _lib.ptr(gt_bboxes), _lib.ptr(num_gt), _lib.ptr(priors),
-        B, P, M, float(alpha), flags,
-        _lib.ptr(mask), _lib.ptr(gt_idx), _lib.ptr(stacked), _lib.ptr(n_stacked),
-        _lib.ptr(d_loc), _lib.ptr(d_conf), _lib.ptr(conf_out), _lib.ptr(results),
-        _lib.ptr(ws), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+    args = (_lib.ptr(locations), _lib.ptr(confidences), _lib.ptr(gt_bboxes), _lib.ptr(num_gt), _lib.ptr(priors),
+            B, P, M, float(alpha), flags,
+            _lib.ptr(mask), _lib.ptr(gt_idx), _lib.ptr(stacked), _lib.ptr(n_stacked),
+            _lib.ptr(d_loc), _lib.ptr(d_conf), _lib.ptr(conf_out), _lib.ptr(results),
+            _lib.ptr(ws), ws.numel())
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    if peer is not None and peer.world > 1:
+        rc = lib.mbx_match_loss_allreduce(*args, peer.ptr_array, peer.world, peer.rank, stream)
+    else:
+        rc = lib.mbx_match_loss(*args, stream)
     _lib.check(rc, "mbx_match_loss")
     return out
 
@@ -196,7 +204,7 @@ class MultiboxLossStep:
     """
 
     def __init__(self, B, P, M, priors, alpha, device="cuda", logits=False, want_mask=False,
-                 want_stacked=False, warps=0, use_graph=False):
+                 want_stacked=False, warps=0, use_graph=False, peer=None):
         self.B, self.P, self.M, self.alpha = B, P, M, float(alpha)
         self.device = torch.device(device)
         if self.device.index is None:
@@ -205,33 +213,38 @@ class MultiboxLossStep:
         self.warps = warps
         self.priors = _f32c(torch.as_tensor(priors).to(self.device), "priors")
         self.want_mask, self.want_stacked = want_mask, want_stacked
+        self.peer = peer if (peer is not None and peer.world > 1) else None
         self.out = {}
         # packed staging: one pinned host buffer, one device buffer, typed views into both
-        n_loc, n_conf, n_gt = B * P * 4, B * P, B * M * 4
-        self._sections = (0, n_loc, n_loc + n_conf, n_loc + n_conf + n_gt, n_loc + n_conf + n_gt + B)
-        words = self._sections[-1]
+        def up4(x):          # every section starts 16-byte aligned
+            return (x + 3) // 4 * 4
+        o_conf = up4(B * P * 4)
+        o_gt = up4(o_conf + B * P)
+        o_ng = up4(o_gt + B * M * 4)
+        self._sections = ((0, B * P * 4), (o_conf, B * P), (o_gt, B * M * 4), (o_ng, B))
+        words = up4(o_ng + B)
         self.h_in = torch.empty((words,), dtype=torch.float32).pin_memory()
         self.d_in = torch.empty((words,), dtype=torch.float32, device=self.device)
         self.h_loc, self.h_conf, self.h_gt, self.h_ng = self._views(self.h_in)
         self.d_loc_in, self.d_conf_in, self.d_gt_in, self.d_ng_in = self._views(self.d_in)
-        self.h_res = torch.empty((8,), dtype=torch.float32).pin_memory()
+        self.h_res = torch.empty((_lib.RESULT_WORDS,), dtype=torch.float32).pin_memory()
         self.h2d_bytes = 4 * words
-        self.d2h_bytes = 32
+        self.d2h_bytes = 4 * _lib.RESULT_WORDS
         self.use_graph = bool(use_graph)
         self._graph = None
         self._launch = None
 
     def _views(self, buf):
-        o = self._sections
+        (a0, n0), (a1, n1), (a2, n2), (a3, n3) = self._sections
         B, P, M = self.B, self.P, self.M
-        return (buf[o[0]:o[1]].view(B, P, 4), buf[o[1]:o[2]].view(B, P), buf[o[2]:o[3]].view(B, M, 4),
-                buf[o[3]:o[4]].view(torch.int32))
+        return (buf[a0:a0 + n0].view(B, P, 4), buf[a1:a1 + n1].view(B, P), buf[a2:a2 + n2].view(B, M, 4),
+                buf[a3:a3 + n3].view(torch.int32))
 
     def step(self, locations, confidences, gt, num_gt):
         return match_loss_raw(locations, confidences.view(self.B, self.P), gt, num_gt, self.priors,
                               self.alpha, flags=self.flags, want_mask=self.want_mask,
                               want_gt_idx=self.want_mask, want_stacked=self.want_stacked,
-                              want_grads=True, warps=self.warps, out=self.out)
+                              want_grads=True, warps=self.warps, out=self.out, peer=self.peer)
 
     def prepare(self, locations, confidences, gt, num_gt):
         """Returns a zero-argument callable that launches the step on these (fixed)
@@ -252,8 +265,12 @@ class MultiboxLossStep:
                 c.c_void_p(out["d_locations"].data_ptr()), c.c_void_p(out["d_confidences"].data_ptr()),
                 c.c_void_p(None), c.c_void_p(out["results"].data_ptr()), c.c_void_p(ws.data_ptr()),
                 c.c_size_t(ws.numel()))
-        fn = lib.mbx_match_loss
         dev = self.device
+        if self.peer is not None:
+            fn = lib.mbx_match_loss_allreduce
+            args = args + (self.peer.ptr_array, self.peer.world, self.peer.rank)
+        else:
+            fn = lib.mbx_match_loss
 
         def launch(_keep=keep):
             rc = fn(*args, c.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
@@ -280,6 +297,12 @@ class MultiboxLossStep:
             with torch.cuda.graph(g, stream=side):
                 self._enqueue_host_step()
             self._graph = g
+
+    def global_losses(self):
+        """(location_loss, confidence_loss) summed over all ranks, from the last step_host /
+        step_pinned (fused all-reduce; equals the local losses on one GPU)."""
+        g = self.h_res[8:12].view(torch.float64)
+        return float(g[0]), float(g[1])
 
     def step_host(self, locations, confidences, gt, num_gt, validate=True):
         """numpy in -> (location_loss, confidence_loss) python floats out; the

@@ -1,0 +1,44 @@
+"""Multi-GPU check of the fused (peer-memory) loss all-reduce, run under torchrun on the GPU box:
+python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 profiles/dist_check.py
+Every rank solves its contiguous shard of one global batch; the fused global losses must equal
+(a) an NCCL all-reduce of the local fp64 losses and (b) the oracle on the whole batch."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from multibox_b200 import dist as mdist  # noqa: E402
+from multibox_b200 import loss, synth  # noqa: E402
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+peer = mdist.PeerAllreduce()
+B = 8 * world + 3
+d = synth.make_train_inputs(K=5, B=B, M=20, seed=4321, edge_cases=True)
+lo, hi = mdist.shard_range(B)
+sh = mdist.shard_batch({k: d[k] for k in ("locations", "confidences", "gt", "num_gt")}, B)
+step = loss.MultiboxLossStep(hi - lo, d["P"], 20, d["priors"], d["alpha"], peer=peer, use_graph=True)
+ok = True
+for it in range(5):       # several steps: exercises both parities and the sequence counter
+    ll, cl = step.step_host(sh["locations"], sh["confidences"], sh["gt"], sh["num_gt"])
+    gl, gc = step.global_losses()
+    t = torch.tensor([ll, cl], dtype=torch.float64, device="cuda")
+    t64 = step.out["results"][4:8].view(torch.float64).clone()
+    dist.all_reduce(t64)
+    ok &= abs(gl - t64[0].item()) <= 1e-12 * abs(gl) and abs(gc - t64[1].item()) <= 1e-12 * abs(gc)
+if rank == 0:
+    from oracle import np_oracle
+    ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], d["alpha"])
+    ok &= abs(gl - ref["location_loss_f64"]) <= 1e-9 * abs(gl) and abs(gc - ref["confidence_loss_f64"]) <= 1e-9 * abs(gc)
+    print("dist_check world=%d: fused global losses %.6f %.6f  oracle %.6f %.6f  -> %s"
+          % (world, gl, gc, ref["location_loss_f64"], ref["confidence_loss_f64"], "OK" if ok else "MISMATCH"))
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)

@@ -133,6 +133,17 @@ def test_step_object_host_path(cuda_device, use_graph):
     np.testing.assert_allclose([ll, cl], [ref2["location_loss"], ref2["confidence_loss"]], rtol=RTOL)
 
 
+def test_step_object_odd_batch(cuda_device):
+    """Packed staging must keep every section 16-byte aligned for any B (found on a 9-image shard)."""
+    for B in (1, 3, 9):
+        d = synth.make_train_inputs(K=5, B=B, M=20, seed=B)
+        step = loss.MultiboxLossStep(B, d["P"], 20, d["priors"], 1000.0, use_graph=True)
+        ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], 1000.0)
+        ll, cl = step.step_host(d["locations"], d["confidences"], d["gt"], d["num_gt"])
+        np.testing.assert_allclose([ll, cl], [ref["location_loss"], ref["confidence_loss"]], rtol=RTOL)
+        assert step.global_losses() == pytest.approx((ref["location_loss_f64"], ref["confidence_loss_f64"]), rel=1e-9)
+
+
 def test_determinism(cuda_device):
     d = synth.make_train_inputs(K=7, B=300, M=100, dist="coco_person", seed=2)
     a = _run_gpu(d, 1000.0)
