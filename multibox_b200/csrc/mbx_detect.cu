@@ -41,13 +41,18 @@ __device__ __forceinline__ float from_orderable(uint32_t o) {
 
 __device__ __forceinline__ float clip01(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); }
 
-// fp32 IoU exactly as oracle/np_oracle.greedy_nms (and torchvision's CPU nms) computes it
+// fp32 IoU test exactly as oracle/np_oracle.greedy_nms (and torchvision's CPU nms) decides it:
+//   fl(inter / ((area_a + area_b) - inter)) > thr.
+// The quotient is first formed with the fast reciprocal (<= 2 ulp off); only when it lands within
+// a few ulp of the threshold is the IEEE division used, so the decision is always the exact one.
 __device__ __forceinline__ bool iou_gt(float4 a, float area_a, float4 b, float area_b, float thr) {
-    float w = fmaxf(0.0f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
-    float h = fmaxf(0.0f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
-    float inter = __fmul_rn(w, h);
-    float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
-    return iou > thr;
+    const float w = fmaxf(0.0f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+    const float h = fmaxf(0.0f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+    const float inter = __fmul_rn(w, h);
+    const float den = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    float q = __fdividef(inter, den);
+    if (fabsf(q - thr) <= 1e-6f * fabsf(thr) || !(fabsf(q) < CUDART_INF_F)) q = __fdiv_rn(inter, den);
+    return q > thr;
 }
 
 struct DSmem {
@@ -186,26 +191,62 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
                 s.sarea[t] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
             }
             __syncthreads();
-            // suppression matrix: bit j of nmask[i][w] <=> j = 32w+bit > i and IoU(i, j) > thr
+            // suppression matrix: bit j of nmask[i][w] <=> j = 32w+bit > i and IoU(i, j) > thr.
+            // Work unit = (column word w, block of 32 rows rb <= w): the lanes keep their column's
+            // box in registers, rows are broadcast from shared memory, one ballot per row.
             const int WS = (KM + 31) >> 5;
-            for (int task = warp; task < kk * W; task += NWARPS) {
-                const int i = task / W, w = task - i * W;
-                if (w < (i >> 5)) continue;
+            const int units = W * (W + 1) / 2;
+            for (int t = warp; t < units; t += NWARPS) {
+                int w = 0;
+                while ((w + 1) * (w + 2) / 2 <= t) ++w;
+                const int rb = t - w * (w + 1) / 2;
                 const int jj = (w << 5) + lane;
-                bool sup = false;
-                if (jj > i && jj < kk) sup = iou_gt(s.sbox[i], s.sarea[i], s.sbox[jj], s.sarea[jj], p.nms_iou);
-                const unsigned bal = __ballot_sync(0xffffffffu, sup);
-                if (lane == 0) s.nmask[i * WS + w] = bal;
+                const bool jvalid = jj < kk;
+                const float4 bj = s.sbox[jvalid ? jj : 0];
+                const float aj = s.sarea[jvalid ? jj : 0];
+                const int i_end = min(kk, (rb << 5) + 32);
+                for (int i = rb << 5; i < i_end; ++i) {
+                    const bool sup = jvalid && jj > i && iou_gt(s.sbox[i], s.sarea[i], bj, aj, p.nms_iou);
+                    const unsigned bal = __ballot_sync(0xffffffffu, sup);
+                    if (lane == 0) s.nmask[i * WS + w] = bal;
+                }
             }
             __syncthreads();
             if (warp == 0) {
-                unsigned rem = 0u, keptw = 0u;   // lane w owns bits [32w, 32w+32)
-                for (int i = 0; i < kk; ++i) {
-                    const int wd = i >> 5;
-                    const unsigned rw = __shfl_sync(0xffffffffu, rem, wd);
-                    if (!((rw >> (i & 31)) & 1u)) {
-                        if (lane == wd) keptw |= 1u << (i & 31);
-                        if (lane >= wd && lane < W) rem |= s.nmask[i * WS + lane];
+                // greedy sweep in score order, one 32-box chunk at a time.  Lane w owns the
+                // "suppressed by an earlier kept box" word of chunk w.  Inside a chunk the kept set
+                // is the unique fixed point of  kept_i = cand_i & !exists kept_j (j<i) suppressing i,
+                // reached by iterating from kept = cand (bit i is final after i+1 rounds).
+                unsigned rem = 0u, keptw = 0u;
+                for (int c = 0; c < W; ++c) {
+                    const int row = (c << 5) + lane;
+                    const unsigned d = (row < kk) ? s.nmask[row * WS + c] : 0u;   // whom box `row` suppresses in this chunk
+                    unsigned tcol = 0u;                                           // who suppresses box `row` in this chunk
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const unsigned bal = __ballot_sync(0xffffffffu, (d >> i) & 1u);
+                        if (lane == i) tcol = bal;
+                    }
+                    const unsigned remc = __shfl_sync(0xffffffffu, rem, c);
+                    const unsigned valid = (kk - (c << 5) >= 32) ? 0xffffffffu : ((1u << (kk - (c << 5))) - 1u);
+                    const unsigned cand = ~remc & valid;
+                    unsigned kept = cand;
+                    for (int it = 0; it < 32; ++it) {
+                        const bool dead = (tcol & kept) != 0u;      // tcol only has bits j < lane
+                        const unsigned nk = __ballot_sync(0xffffffffu, !dead) & cand;
+                        if (nk == kept) break;
+                        kept = nk;
+                    }
+                    if (lane == c) keptw = kept;
+                    // propagate the kept boxes' suppression to the later chunks
+                    if (lane > c && lane < W) {
+                        unsigned k = kept, acc = 0u;
+                        while (k) {
+                            const int i = __ffs(k) - 1;
+                            k &= k - 1u;
+                            acc |= s.nmask[((c << 5) + i) * WS + lane];
+                        }
+                        rem |= acc;
                     }
                 }
                 // exclusive prefix of kept counts per word

@@ -170,3 +170,106 @@ def eval_topk(locs, confs, bbox_priors, input_size, image_ids, k=100):
             x1, y1, x2, y2 = boxes[b, t]
             rows.append([int(ids[b]), x1, y1, x2 - x1, y2 - y1, float(scores[b, t]), 1])
     return rows
+
+
+class DetectStep:
+    """Allocation-free detection post-processing object for callers that hold HOST arrays
+    (reference detect.py:395-443 pulls the head outputs to the host): inputs are staged in ONE
+    packed pinned buffer (one H2D copy), outputs come back in ONE packed buffer (one D2H copy),
+    and copy + kernel + copy are replayed as a CUDA graph.
+
+    Packed input layout (4-byte words, each section 16-byte aligned):
+      locations B*P*4 | confidences B*P | restrictions B*4 | max_to_keep B | offsets B*2 |
+      patch_dims B*2 | image_dims B*2 | is_flipped B
+    Packed output layout: boxes f64 B*k*4 | scores f32 B*k | prior_idx i32 B*k | count i32 B
+    """
+
+    IN_FIELDS = (("locations", 4, torch.float32), ("confidences", 1, torch.float32),
+                 ("restrictions", 4, torch.float32), ("max_to_keep", 1, torch.int32),
+                 ("offsets", 2, torch.int32), ("patch_dims", 2, torch.int32),
+                 ("image_dims", 2, torch.int32), ("is_flipped", 1, torch.int32))
+
+    def __init__(self, B, P, k_max, priors, nms_iou=None, device="cuda", logits=False, use_graph=True, warps=0):
+        self.B, self.P, self.k = int(B), int(P), int(k_max)
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.priors = _f32c(torch.as_tensor(priors).to(self.device), "priors")
+        self.nms_iou, self.logits, self.warps, self.use_graph = nms_iou, logits, warps, use_graph
+
+        def up4(x):
+            return (x + 3) // 4 * 4
+        off, self._in = 0, {}
+        for name, per, dt in self.IN_FIELDS:
+            n = self.B * (self.P * per if name in ("locations", "confidences") else per)
+            self._in[name] = (off, n, dt)
+            off = up4(off + n)
+        self.h_in = torch.empty((off,), dtype=torch.float32).pin_memory()
+        self.d_in = torch.empty((off,), dtype=torch.float32, device=self.device)
+        k = self.k
+        o_sc = 2 * self.B * k * 4                       # after the float64 boxes (in 4-byte words)
+        o_idx = up4(o_sc + self.B * k)
+        o_cnt = up4(o_idx + self.B * k)
+        words = up4(o_cnt + self.B)
+        self._out = (o_sc, o_idx, o_cnt)
+        self.h_out = torch.empty((words,), dtype=torch.float32).pin_memory()
+        self.d_out = torch.empty((words,), dtype=torch.float32, device=self.device)
+        self.h2d_bytes, self.d2h_bytes = 4 * off, 4 * words
+        self._graph = None
+        self._ready = False
+
+    def view_in(self, buf, name):
+        off, n, dt = self._in[name]
+        t = buf[off:off + n]
+        return t if dt == torch.float32 else t.view(dt)
+
+    def views_out(self, buf):
+        B, k = self.B, self.k
+        o_sc, o_idx, o_cnt = self._out
+        return {"boxes": buf[:o_sc].view(torch.float64).view(B, k, 4), "scores": buf[o_sc:o_sc + B * k].view(B, k),
+                "prior_idx": buf[o_idx:o_idx + B * k].view(torch.int32).view(B, k),
+                "count": buf[o_cnt:o_cnt + B].view(torch.int32)}
+
+    def fill_host(self, **arrays):
+        """Writes numpy arrays into the pinned staging buffer."""
+        import numpy as np
+        for name, a in arrays.items():
+            dst = self.view_in(self.h_in, name).numpy()
+            np.copyto(dst, np.ascontiguousarray(a).reshape(dst.shape))
+
+    def _enqueue(self):
+        B, P = self.B, self.P
+        self.d_in.copy_(self.h_in, non_blocking=True)
+        v = lambda n: self.view_in(self.d_in, n)   # noqa: E731
+        postprocess(v("locations").view(B, P, 4), v("confidences").view(B, P), self.priors,
+                    restrictions=v("restrictions").view(B, 4), max_to_keep=v("max_to_keep"),
+                    offsets=v("offsets").view(B, 2), patch_dims=v("patch_dims").view(B, 2),
+                    image_dims=v("image_dims").view(B, 2), is_flipped=v("is_flipped"), nms_iou=self.nms_iou,
+                    k_max=self.k, logits=self.logits, want_patch_boxes=False, warps=self.warps,
+                    out=self.views_out(self.d_out))
+        self.h_out.copy_(self.d_out, non_blocking=True)
+
+    def run_pinned(self):
+        """H2D of the packed inputs, one kernel, D2H of the packed outputs, sync.  Returns the
+        dict of HOST views (boxes f64 [B,k,4], scores, prior_idx, count)."""
+        if not self._ready:
+            self._enqueue()
+            torch.cuda.current_stream(self.device).synchronize()
+            self._ready = True
+            if self.use_graph:
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    self._enqueue()
+                self._graph = g
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._enqueue()
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.views_out(self.h_out)
+
+    def run_host(self, **arrays):
+        self.fill_host(**arrays)
+        return self.run_pinned()

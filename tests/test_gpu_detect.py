@@ -144,3 +144,22 @@ def test_full_size_properties(cuda_device):
         assert len(np_oracle.greedy_nms(out["patch_boxes"][b, :c], nms)) == c
     out2 = _run(d, nms_iou=nms)
     assert np.array_equal(out["prior_idx"], out2["prior_idx"])
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_detect_step_host_path(cuda_device, use_graph):
+    d = synth.make_detect_inputs(K=5, B=9, keep=60, seed=21, patches=True)      # odd B: section alignment
+    names = ("locations", "confidences", "restrictions", "max_to_keep", "offsets", "patch_dims", "image_dims",
+             "is_flipped")
+    step = detect.DetectStep(9, d["P"], 60, d["priors"], nms_iou=0.5, use_graph=use_graph)
+    post = np_oracle.postprocess(d["locations"], d["confidences"], d["priors"], d["restrictions"],
+                                 d["max_to_keep"], d["offsets"], d["patch_dims"], d["image_dims"],
+                                 d["is_flipped"], nms_iou=0.5)
+    for _ in range(3):
+        out = step.run_host(**{k: d[k] for k in names})
+        for b, m in enumerate(post):
+            c = m["boxes"].shape[0]
+            assert out["count"][b].item() == c
+            assert np.array_equal(out["prior_idx"][b, :c].numpy(), m["prior_idx"])
+            assert np.array_equal(out["boxes"][b, :c].numpy(), m["boxes"])
+            assert np.array_equal(out["scores"][b, :c].numpy(), m["scores"])
