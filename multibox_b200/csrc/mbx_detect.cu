@@ -17,6 +17,20 @@
 
 #include "mbx_common.cuh"
 
+// Optional phase timing (profiles/phase_timing.py --detect builds with -DMBX_PHASE_TIMING).
+#ifdef MBX_PHASE_TIMING
+#define MBX_DT(k)                                        \
+    do {                                                 \
+        const long long t_now__ = clock64();             \
+        t_acc[k] += t_now__ - t_last;                    \
+        t_last = t_now__;                                \
+    } while (0)
+#else
+#define MBX_DT(k) \
+    do {          \
+    } while (0)
+#endif
+
 namespace mbx {
 
 struct DetectParams {
@@ -43,21 +57,38 @@ __device__ __forceinline__ float clip01(float x) { return x < 0.0f ? 0.0f : (x >
 
 // fp32 IoU test exactly as oracle/np_oracle.greedy_nms (and torchvision's CPU nms) decides it:
 //   fl(inter / ((area_a + area_b) - inter)) > thr.
-// The quotient is first formed with the fast reciprocal (<= 2 ulp off); only when it lands within
-// a few ulp of the threshold is the IEEE division used, so the decision is always the exact one.
-__device__ __forceinline__ bool iou_gt(float4 a, float area_a, float4 b, float area_b, float thr) {
+// iou_fast forms the quotient with the fast reciprocal (<= 2 ulp off) and reports `near` when it
+// lands within a few ulp of the threshold; only those (rare) pairs are re-decided with the IEEE
+// division (iou_exact), so the final decision is always the exact one without a branch in the
+// common path.
+__device__ __forceinline__ bool iou_fast(float4 a, float area_a, float4 b, float area_b, float thr, bool &near) {
     const float w = fmaxf(0.0f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
     const float h = fmaxf(0.0f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
     const float inter = __fmul_rn(w, h);
     const float den = __fsub_rn(__fadd_rn(area_a, area_b), inter);
-    float q = __fdividef(inter, den);
-    if (fabsf(q - thr) <= 1e-6f * fabsf(thr) || !(fabsf(q) < CUDART_INF_F)) q = __fdiv_rn(inter, den);
+    const float q = __fdividef(inter, den);
+    near = fabsf(q - thr) <= 1e-6f * fabsf(thr);
     return q > thr;
+}
+__device__ __noinline__ bool iou_exact(float4 a, float area_a, float4 b, float area_b, float thr) {
+    const float w = fmaxf(0.0f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+    const float h = fmaxf(0.0f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+    const float inter = __fmul_rn(w, h);
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter)) > thr;
+}
+
+constexpr int kBins = 1024;   // confidence histogram used to pre-select the top max_to_keep
+__device__ __forceinline__ int conf_bin(float c) {
+    // monotone non-decreasing in the sort order of c (any float); NaN sorts first like numpy's
+    if (c != c) return kBins - 1;
+    const float t = fminf(fmaxf(c * static_cast<float>(kBins), 0.0f), static_cast<float>(kBins - 1));
+    return static_cast<int>(t);
 }
 
 struct DSmem {
     float4 *priors, *box, *sbox;
-    unsigned long long *keys;
+    unsigned long long *keys, *ckeys;
+    int *hist;
     float *sarea;
     uint32_t *nmask, *keepw;
     int *keeppre, *cnt;
@@ -79,17 +110,21 @@ __host__ __device__ inline size_t dcarve(DSmem *s, unsigned char *base, int P, i
     size_t o_box = take(sizeof(float4) * P, 16);
     size_t o_sbox = take(nms ? sizeof(float4) * k_max : 0, 16);
     size_t o_keys = take(sizeof(unsigned long long) * n2, 8);
+    size_t o_ckeys = take(sizeof(unsigned long long) * n2, 8);
     size_t o_bar = take(8, 8);
+    size_t o_hist = take(sizeof(int) * kBins, 4);
     size_t o_area = take(nms ? sizeof(float) * k_max : 0, 4);
     size_t o_nm = take(nms ? sizeof(uint32_t) * static_cast<size_t>(k_max) * W : 0, 4);
     size_t o_kw = take(sizeof(uint32_t) * 32, 4);
     size_t o_kp = take(sizeof(int) * 33, 4);
-    size_t o_cnt = take(sizeof(int) * 2, 4);
+    size_t o_cnt = take(sizeof(int) * 4, 4);
     if (s) {
         s->priors = reinterpret_cast<float4 *>(base + o_pri);
         s->box = reinterpret_cast<float4 *>(base + o_box);
         s->sbox = reinterpret_cast<float4 *>(base + o_sbox);
         s->keys = reinterpret_cast<unsigned long long *>(base + o_keys);
+        s->ckeys = reinterpret_cast<unsigned long long *>(base + o_ckeys);
+        s->hist = reinterpret_cast<int *>(base + o_hist);
         s->bar = reinterpret_cast<uint64_t *>(base + o_bar);
         s->sarea = reinterpret_cast<float *>(base + o_area);
         s->nmask = reinterpret_cast<uint32_t *>(base + o_nm);
@@ -98,6 +133,83 @@ __host__ __device__ inline size_t dcarve(DSmem *s, unsigned char *base, int P, i
         s->cnt = reinterpret_cast<int *>(base + o_cnt);
     }
     return dalign(o, 16);
+}
+
+// Descending bitonic sort of N = T*R 64-bit keys held R per thread (thread `tid` owns elements
+// tid*R .. tid*R+R-1).  Compare-exchange distances below R run in registers, below 32*R with warp
+// shuffles; only the distances that cross warps go through shared memory (9 barriers for
+// N = 1024 on 256 threads instead of the 55 of an all-shared-memory sort).  On return the
+// sorted keys are in `sm[0..N)` (and in the registers).
+template <int T, int R>
+__device__ __forceinline__ void block_sort_desc(unsigned long long (&k)[R], unsigned long long *sm, int tid) {
+    constexpr int N = T * R;
+#pragma unroll
+    for (int kk = 2; kk <= N; kk <<= 1) {
+        bool in_smem = false;
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            if (j >= 32 * R) {
+                if (!in_smem) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) sm[tid * R + r] = k[r];
+                    __syncthreads();
+                    in_smem = true;
+                }
+                for (int t = tid; t < (N >> 1); t += T) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int ixj = i | j;
+                    const unsigned long long a = sm[i], c = sm[ixj];
+                    const bool desc = (i & kk) == 0;
+                    if ((a < c) == desc) {
+                        sm[i] = c;
+                        sm[ixj] = a;
+                    }
+                }
+                __syncthreads();
+            } else {
+                if (in_smem) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) k[r] = sm[tid * R + r];
+                    in_smem = false;
+                }
+                if (j >= R) {
+                    const int lm = j / R;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[r], lm);
+                        const int e = tid * R + r;
+                        const bool keep_max = (((e & kk) == 0) == ((e & j) == 0));
+                        const unsigned long long mx = k[r] > o ? k[r] : o, mn = k[r] > o ? o : k[r];
+                        k[r] = keep_max ? mx : mn;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if ((r & j) == 0) {
+                            const int e = tid * R + r;
+                            const bool desc = (e & kk) == 0;
+                            const unsigned long long a = k[r], c = k[r | j];
+                            const unsigned long long mx = a > c ? a : c, mn = a > c ? c : a;
+                            k[r] = desc ? mx : mn;
+                            k[r | j] = desc ? mn : mx;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();   // everyone is done reading sm from the last cross-warp phase
+#pragma unroll
+    for (int r = 0; r < R; ++r) sm[tid * R + r] = k[r];
+    __syncthreads();
+}
+
+template <int T, int R>
+__device__ __forceinline__ void sort_keys_in_smem(unsigned long long *sm, int tid) {
+    unsigned long long k[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) k[r] = sm[tid * R + r];
+    block_sort_desc<T, R>(k, sm, tid);
 }
 
 template <int NWARPS>
@@ -121,6 +233,10 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
         bulk_copy_g2s(s.priors, p.priors, static_cast<uint32_t>(sizeof(float4) * P), s.bar);
     }
     bool priors_ready = false;
+#ifdef MBX_PHASE_TIMING
+    long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_last = clock64();
+#endif
 
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         if (!priors_ready) {
@@ -130,7 +246,11 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
         const size_t row0 = static_cast<size_t>(b) * P;
         float4 r = make_float4(0.f, 0.f, 1.f, 1.f);
         if (p.restrictions) r = reinterpret_cast<const float4 *>(p.restrictions)[b];
-        if (tid == 0) s.cnt[0] = 0;
+        if (tid == 0) {
+            s.cnt[0] = 0;
+            s.cnt[2] = 0;
+        }
+        for (int t = tid; t < kBins; t += T) s.hist[t] = 0;
         __syncthreads();
         // ---- decode + clip + restriction filter + sort key
         const float4 *gl = reinterpret_cast<const float4 *>(p.locations) + row0;
@@ -151,6 +271,7 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
                 const bool drop = (l.x < r.x) || (l.y < r.y) || (l.z > r.z) || (l.w > r.w);   // detect.py:92-99
                 if (!drop) {
                     key = (static_cast<unsigned long long>(orderable(c)) << 32) | static_cast<unsigned>(j);
+                    atomicAdd(&s.hist[conf_bin(c)], 1);
                     ++mine;
                 }
             }
@@ -158,35 +279,101 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
         }
         if (mine) atomicAdd(&s.cnt[0], mine);
         __syncthreads();
-        // ---- bitonic sort, descending
-        for (int k = 2; k <= N2; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < (N2 >> 1); t += T) {
-                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    const int ixj = i | j;
-                    const unsigned long long a = s.keys[i], c = s.keys[ixj];
-                    const bool desc = (i & k) == 0;
-                    if ((a < c) == desc) {
-                        s.keys[i] = c;
-                        s.keys[ixj] = a;
-                    }
-                }
-                __syncthreads();
-            }
-        }
-        int kk = s.cnt[0];
+        MBX_DT(0);   // load / decode / keys
+        // ---- pre-selection: only keys whose confidence bin reaches the bin of the keep-th largest
+        // can be in the top max_to_keep; sort just those (typically ~keep of P) instead of all P.
         int keep = KM;
         if (p.max_to_keep) {
             keep = p.max_to_keep[b];
             keep = keep < 0 ? 0 : (keep > KM ? KM : keep);
         }
-        kk = kk < keep ? kk : keep;
+        const int n_valid = s.cnt[0];
+        const int target = n_valid < keep ? n_valid : keep;
+        if (warp == 0) {
+            // lane l owns bins [hi-31, hi], hi = kBins-1-32*l (lane 0 = the largest confidences)
+            const int hi = kBins - 1 - 32 * lane;
+            int part = 0;
+#pragma unroll 8
+            for (int t = 0; t < 32; ++t) part += s.hist[hi - t];
+            int cum = part;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, cum, o);
+                if (lane >= o) cum += u;
+            }
+            const unsigned reach = __ballot_sync(0xffffffffu, cum >= target);
+            int tb = 0;
+            if (reach && target > 0) {
+                const int l0 = __ffs(reach) - 1;
+                if (lane == l0) {
+                    int run = cum - part;
+                    tb = hi;
+                    for (int t = 0; t < 32; ++t) {
+                        run += s.hist[hi - t];
+                        tb = hi - t;
+                        if (run >= target) break;
+                    }
+                }
+                tb = __shfl_sync(0xffffffffu, tb, l0);
+            }
+            if (lane == 0) s.cnt[1] = (target > 0) ? tb : kBins;   // nothing to keep: select nothing
+        }
+        __syncthreads();
+        const int tb = s.cnt[1];
+        for (int j0 = 0; j0 < P; j0 += T) {
+            const int j = j0 + tid;
+            unsigned long long key = 0ull;
+            bool take = false;
+            if (j < P) {
+                key = s.keys[j];
+                take = key != 0ull && conf_bin(from_orderable(static_cast<uint32_t>(key >> 32))) >= tb;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, take);
+            int base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&s.cnt[2], __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (take) s.ckeys[base + __popc(bal & ((1u << lane) - 1u))] = key;
+        }
+        __syncthreads();
+        const int nc = s.cnt[2];
+        int n2c = T;
+        while (n2c < nc) n2c <<= 1;
+        for (int t = nc + tid; t < n2c; t += T) s.ckeys[t] = 0ull;
+        __syncthreads();
+        // ---- descending sort of the candidates (registers + shuffles; shared memory across warps)
+        if (n2c == T)
+            sort_keys_in_smem<T, 1>(s.ckeys, tid);
+        else if (n2c == 2 * T)
+            sort_keys_in_smem<T, 2>(s.ckeys, tid);
+        else if (n2c == 4 * T)
+            sort_keys_in_smem<T, 4>(s.ckeys, tid);
+        else if (n2c == 8 * T)
+            sort_keys_in_smem<T, 8>(s.ckeys, tid);
+        else {
+            for (int k = 2; k <= n2c; k <<= 1) {      // generic fallback, all in shared memory
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < (n2c >> 1); t += T) {
+                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        const int ixj = i | j;
+                        const unsigned long long a = s.ckeys[i], c = s.ckeys[ixj];
+                        const bool desc = (i & k) == 0;
+                        if ((a < c) == desc) {
+                            s.ckeys[i] = c;
+                            s.ckeys[ixj] = a;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        MBX_DT(1);   // select + sort
+        const int kk = target;
         int count = kk;
         // ---- greedy NMS over the kk sorted survivors (extension)
         if (nms) {
             const int W = (kk + 31) >> 5;
             for (int t = tid; t < kk; t += T) {
-                const float4 bx = s.box[static_cast<unsigned>(s.keys[t] & 0xffffffffu)];
+                const float4 bx = s.box[static_cast<unsigned>(s.ckeys[t] & 0xffffffffu)];
                 s.sbox[t] = bx;
                 s.sarea[t] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
             }
@@ -204,14 +391,40 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
                 const bool jvalid = jj < kk;
                 const float4 bj = s.sbox[jvalid ? jj : 0];
                 const float aj = s.sarea[jvalid ? jj : 0];
-                const int i_end = min(kk, (rb << 5) + 32);
-                for (int i = rb << 5; i < i_end; ++i) {
-                    const bool sup = jvalid && jj > i && iou_gt(s.sbox[i], s.sarea[i], bj, aj, p.nms_iou);
-                    const unsigned bal = __ballot_sync(0xffffffffu, sup);
-                    if (lane == 0) s.nmask[i * WS + w] = bal;
+                const int i0 = rb << 5;
+                constexpr int RU = 8;   // rows per batch: RU independent IoU chains per lane
+                for (int ib = 0; ib < 32; ib += RU) {
+                    bool sup[RU], near[RU];
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) {
+                        const int i = i0 + ib + u;
+                        const int ic = i < kk ? i : 0;
+                        const bool act = jvalid && jj > i && i < kk;
+                        bool nr;
+                        const bool sp = iou_fast(s.sbox[ic], s.sarea[ic], bj, aj, p.nms_iou, nr);
+                        sup[u] = sp && act;
+                        near[u] = nr && act;
+                    }
+                    bool any_near = false;
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) any_near |= near[u];
+                    if (__any_sync(0xffffffffu, any_near)) {   // rare: a quotient within ulps of thr
+#pragma unroll
+                        for (int u = 0; u < RU; ++u) {
+                            const int i = i0 + ib + u;
+                            if (near[u]) sup[u] = iou_exact(s.sbox[i], s.sarea[i], bj, aj, p.nms_iou);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) {
+                        const int i = i0 + ib + u;
+                        const unsigned bal = __ballot_sync(0xffffffffu, sup[u]);
+                        if (lane == u && i < kk) s.nmask[i * WS + w] = bal;
+                    }
                 }
             }
             __syncthreads();
+            MBX_DT(2);   // suppression matrix
             if (warp == 0) {
                 // greedy sweep in score order, one 32-box chunk at a time.  Lane w owns the
                 // "suppressed by an earlier kept box" word of chunk w.  Inside a chunk the kept set
@@ -238,15 +451,13 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
                         kept = nk;
                     }
                     if (lane == c) keptw = kept;
-                    // propagate the kept boxes' suppression to the later chunks
-                    if (lane > c && lane < W) {
-                        unsigned k = kept, acc = 0u;
-                        while (k) {
-                            const int i = __ffs(k) - 1;
-                            k &= k - 1u;
-                            acc |= s.nmask[((c << 5) + i) * WS + lane];
-                        }
-                        rem |= acc;
+                    // propagate the kept boxes' suppression to the later chunks: lanes = rows of this
+                    // chunk, one OR-reduction per later word (lane w keeps word w)
+                    const bool my_kept = (kept >> lane) & 1u;
+                    for (int w = c + 1; w < W; ++w) {
+                        const unsigned m = my_kept ? s.nmask[row * WS + w] : 0u;
+                        const unsigned orw = __reduce_or_sync(0xffffffffu, m);
+                        if (lane == w) rem |= orw;
                     }
                 }
                 // exclusive prefix of kept counts per word
@@ -263,6 +474,7 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
             }
             __syncthreads();
             count = s.keeppre[32];
+            MBX_DT(3);   // sweep (+ wait)
         }
         // ---- store (convert_proposals in float64)
         double sx = 1.0, sy = 1.0, ox = 0.0, oy = 0.0;
@@ -282,7 +494,7 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
                 float sc = 0.f;
                 int idx = -1;
                 if (t < kk) {
-                    const unsigned long long key = s.keys[t];
+                    const unsigned long long key = s.ckeys[t];
                     idx = static_cast<int>(key & 0xffffffffu);
                     sc = from_orderable(static_cast<uint32_t>(key >> 32));
                     bx = s.box[idx];
@@ -320,7 +532,7 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
                     pos = s.keeppre[t >> 5] + __popc(wbits & ((1u << (t & 31)) - 1u));
                 }
                 if (kept) {
-                    const unsigned long long key = s.keys[t];
+                    const unsigned long long key = s.ckeys[t];
                     const int idx = static_cast<int>(key & 0xffffffffu);
                     const float sc = from_orderable(static_cast<uint32_t>(key >> 32));
                     const float4 bx = s.sbox[t];
@@ -357,7 +569,14 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
         }
         if (tid == 0 && p.out_count) p.out_count[b] = count;
         __syncthreads();   // shared state is reused by the next image
+        MBX_DT(4);   // store
     }
+#ifdef MBX_PHASE_TIMING
+    if (lane == 0 && p.out_scores) {
+        long long *dbg = reinterpret_cast<long long *>(p.out_scores) + (static_cast<size_t>(blockIdx.x) * NWARPS + warp) * 8;
+        for (int k = 0; k < 8; ++k) dbg[k] = t_acc[k];
+    }
+#endif
 }
 
 template <int NWARPS>
@@ -548,7 +767,9 @@ extern "C" int mbx_detect(const float *locations, const float *confidences, cons
     p.B = B;
     p.P = P;
     p.k_max = k_max;
-    int n2 = 64;
+    int nwarps = static_cast<int>((flags >> MBX_FLAG_WARPS_SHIFT) & 0xffu);
+    if (nwarps == 0) nwarps = 8;
+    int n2 = nwarps * 32;            // at least one key per thread (register/shuffle sort)
     while (n2 < P) n2 <<= 1;
     p.n2 = n2;
     p.nms_iou = nms_iou;
@@ -564,8 +785,6 @@ extern "C" int mbx_detect(const float *locations, const float *confidences, cons
                   max_smem_optin());
         return MBX_E_TOO_LARGE;
     }
-    int nwarps = static_cast<int>((flags >> MBX_FLAG_WARPS_SHIFT) & 0xffu);
-    if (nwarps == 0) nwarps = 8;
     switch (nwarps) {
         case 4: return launch_detect<4>(p, smem, st);
         case 8: return launch_detect<8>(p, smem, st);

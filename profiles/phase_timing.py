@@ -23,13 +23,41 @@ _build.needs_build = lambda: False
 lib = _lib.load()
 from multibox_b200 import loss  # noqa: E402
 
+detect_mode = "--detect" in sys.argv
+if detect_mode:
+    sys.argv.remove("--detect")
 warps = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
 names = ["prologue", "batched 1st step", "sequential rows", "general scan", "general argmin", "select/log/walk", "(loop exit)", "epilogue"]
 
 
 def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
+
+if detect_mode:
+    from multibox_b200 import detect
+    dn = ["load/decode/keys", "sort", "suppression matrix", "sweep (+wait)", "store"]
+    for label, kw in (("cfg3", dict(K=5, B=148, keep=200, seed=1003)), ("K=11", dict(K=11, B=148, keep=200, seed=4))):
+        q = synth.make_detect_inputs(**kw)
+        B = q["B"]
+        out = {"scores": torch.zeros((B, max(200, 8 * 8 * 2 * 2)), dtype=torch.float32, device="cuda")}
+        for _ in range(2):
+            detect.postprocess(dev(q["locations"]), dev(q["confidences"]), dev(q["priors"]),
+                               restrictions=dev(q["restrictions"]), max_to_keep=dev(q["max_to_keep"]),
+                               offsets=dev(q["offsets"]), patch_dims=dev(q["patch_dims"]),
+                               image_dims=dev(q["image_dims"]), is_flipped=dev(q["is_flipped"]), nms_iou=0.5,
+                               k_max=200, out=out)
+        torch.cuda.synchronize()
+        t = out["scores"].cpu().numpy().reshape(-1).view(np.int64)[:B * 8 * 8].reshape(B, 8, 8)
+        print("detect %s: per-warp mean cycles by phase (block 0; warp 0 / other warps)" % label)
+        for k, nm in enumerate(dn):
+            print("   %-20s %9.0f %9.0f" % (nm, t[0, 0, k], t[0, 1:, k].mean()))
+        print("   total %.0f" % t[0, 0].sum())
+    sys.exit(0)
 
 for label, d in (("cfg2", synth.make_train_inputs(**synth.TRAIN_CONFIGS["cfg2"])),
                  ("cfg2 full n=20", synth.make_train_inputs(K=5, B=32, M=20, dist="full", seed=5))):
