@@ -53,6 +53,13 @@ struct RSmem {
     uint2 *rowpart;             // [M][NWARPS] per-warp first-step minimum of each row {key32, column | tie<<31}
     uint2 *rowmin;              // [M] block-wide first-step minimum of each row
     short *row4col;
+    // per-column state of the general search (touched only for conflict / tie rows, so it lives
+    // in shared memory and the hot first-step pass keeps the registers)
+    double *cv;                 // [P] column dual v
+    double *spc;                // [P] shortest path cost when it is not simply (double)c0 (bit in `dbl`)
+    float *c0;                  // [P] cost of the column against the row being searched (first step)
+    short *pmv;                 // [P] visit index of the row that set spc (bit in `updm`)
+    short *arow;                // [P] row the column was assigned to when it was scanned
     unsigned char *dirty;       // [P] column dual is non-zero
     uint64_t *bar;
 };
@@ -71,6 +78,8 @@ __host__ __device__ inline size_t rcarve(RSmem *s, unsigned char *base, int P, i
     size_t o_part = take(sizeof(int4) * 2 * nwarps, 16);
     size_t o_rp = take(sizeof(uint2) * static_cast<size_t>(Mx) * nwarps, 8);
     size_t o_rm = take(sizeof(uint2) * Mx, 8);
+    size_t o_cv = take(sizeof(double) * P, 8);
+    size_t o_spc = take(sizeof(double) * P, 8);
     size_t o_u = take(sizeof(double) * Mx, 8);
     size_t o_red = take(sizeof(double) * 3 * nwarps, 8);
     size_t o_pk = take(sizeof(unsigned long long) * nwarps, 8);
@@ -82,7 +91,10 @@ __host__ __device__ inline size_t rcarve(RSmem *s, unsigned char *base, int P, i
     size_t o_vis = take(sizeof(int) * (M + 2), 4);
     size_t o_ri = take(sizeof(int) * nwarps, 4);
     size_t o_ctl = take(sizeof(int) * 4, 4);
+    size_t o_c0 = take(sizeof(float) * P, 4);
     size_t o_r4c = take(sizeof(short) * P, 2);
+    size_t o_pmv = take(sizeof(short) * P, 2);
+    size_t o_arow = take(sizeof(short) * P, 2);
     size_t o_dirty = take(P, 1);
     if (s) {
         s->priors = reinterpret_cast<float4 *>(base + o_pri);
@@ -103,6 +115,11 @@ __host__ __device__ inline size_t rcarve(RSmem *s, unsigned char *base, int P, i
         s->rowmin = reinterpret_cast<uint2 *>(base + o_rm);
         s->ctl = reinterpret_cast<int *>(base + o_ctl);
         s->dirty = base + o_dirty;
+        s->cv = reinterpret_cast<double *>(base + o_cv);
+        s->spc = reinterpret_cast<double *>(base + o_spc);
+        s->c0 = reinterpret_cast<float *>(base + o_c0);
+        s->pmv = reinterpret_cast<short *>(base + o_pmv);
+        s->arow = reinterpret_cast<short *>(base + o_arow);
     }
     return align_up(o, 16);
 }
@@ -164,9 +181,46 @@ __device__ __forceinline__ void warp_argmin(unsigned &hi, unsigned &lo, unsigned
 
 }  // namespace
 
+// Per-column state of the GENERAL search (dual v, path cost, first-step cost, path tag, row at
+// removal).  With few columns per thread (C <= 3: the wide, latency-oriented CTAs) it stays in
+// registers; with many it lives in shared memory so that the hot first-step pass keeps the
+// registers (more CTAs per SM).  Each column is only ever touched by its owner thread.
+template <typename TV, int C, bool IN_REGS>
+struct ColState {
+    TV r[IN_REGS ? C : 1];
+    __device__ __forceinline__ TV get(int c, int j, const TV *m) const {
+        if constexpr (IN_REGS) {
+            TV v = r[0];
+#pragma unroll
+            for (int q = 1; q < C; ++q) v = (q == c) ? r[q] : v;
+            return v;
+        } else {
+            return m[j];
+        }
+    }
+    __device__ __forceinline__ void set(int c, int j, TV *m, TV v) {
+        if constexpr (IN_REGS) {
+#pragma unroll
+            for (int q = 0; q < C; ++q)
+                if (q == c) r[q] = v;
+        } else {
+            m[j] = v;
+        }
+    }
+};
+
+// Register budget: aim at >= 16 resident warps per SM (<= 128 registers per thread) while a
+// thread owns few columns; wide per-thread footprints (C >= 5) trade occupancy for registers.
 template <int NWARPS, int C>
-__global__ void __launch_bounds__(NWARPS * 32, 1) mbx_match_loss_reg_kernel(const MatchParams p) {
+constexpr int min_blocks_per_sm() {
+    const int warps_per_sm = (C <= 4) ? 16 : ((C <= 6) ? 12 : 8);
+    return (NWARPS >= warps_per_sm) ? 1 : warps_per_sm / NWARPS;
+}
+
+template <int NWARPS, int C>
+__global__ void __launch_bounds__(NWARPS * 32, min_blocks_per_sm<NWARPS, C>()) mbx_match_loss_reg_kernel(const MatchParams p) {
     constexpr int T = NWARPS * 32;
+    constexpr bool RS = (C <= 3);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RSmem s;
     const bool boundary = (p.flags & MBX_FLAG_BOUNDARY) != 0;
@@ -216,10 +270,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mbx_match_loss_reg_kernel(cons
         // ---- per-column state in registers
         float4 loc[C];
         float lc[C], l1[C], cf[C];
-        float c0[C];          // cost of the column against row `cur` (first Dijkstra step), fp32
-        double v[C];          // column dual
-        double spc64[C];      // shortest path cost when it is not simply (double)c0[c] (bit in `dbl`)
-        int pm[C], arow[C];   // visit index of the row that set spc64 (bit in `updm`); row at removal
+        ColState<double, C, RS> cv, spc;    // dual v; path cost when it is not simply (double)c0 (bit in `dbl`)
+        ColState<float, C, RS> c0;          // first-step cost against the row being searched
+        ColState<short, C, RS> ptag, arow;   // path tag (bit in `updm`); row the column had when scanned
         unsigned vnz = 0u;    // which of this thread's columns have a non-zero dual
         const float4 *gl = reinterpret_cast<const float4 *>(p.locations) + row0;
 #pragma unroll
@@ -235,11 +288,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mbx_match_loss_reg_kernel(cons
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = tid + c * T;
-            v[c] = 0.0;
-            spc64[c] = INF;
-            c0[c] = CUDART_INF_F;
-            pm[c] = 0;
-            arow[c] = -1;
+            if (RS || j < P) {
+                cv.set(c, j, s.cv, 0.0);
+                arow.set(c, j, s.arow, static_cast<short>(-1));
+            }
             if (j < P) {
                 if (has_priors) {
                     const float4 q = s.priors[j];
@@ -346,19 +398,38 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mbx_match_loss_reg_kernel(cons
         // with the general shortest-augmenting-path search below.
         int cur = 0;
         for (;;) {
-            if (tid == 0) {
+            if (warp == 0) {
+                // Warp 0 disposes of up to 32 consecutive rows per round: lane r takes row cur+r.
+                // A row is decisive when its first-step minimum is unique, finite, at a column with
+                // zero dual that is unassigned AND not wanted by an earlier row of the same round.
+                // The round commits the rows before the first non-decisive one.
                 const bool fast_off = s.ctl[1] != 0;
                 while (cur < n && !fast_off) {
-                    const uint2 rm = s.rowmin[cur];
-                    const unsigned col = rm.y & kColNone;
-                    if ((rm.y >> 31) || rm.x >= kOrdInf32 || col == kColNone) break;   // tie / infeasible
-                    if (s.dirty[col] || s.row4col[col] >= 0) break;                    // dual set / conflict
-                    s.row4col[col] = static_cast<short>(cur);
-                    s.col4row[cur] = static_cast<int>(col);
-                    s.u[cur] = static_cast<double>(unord32(rm.x));
-                    ++cur;
+                    const int row = cur + lane;
+                    bool good = false;
+                    unsigned col = kColNone;
+                    uint2 rm = make_uint2(0u, 0u);
+                    if (row < n) {
+                        rm = s.rowmin[row];
+                        col = rm.y & kColNone;
+                        good = !(rm.y >> 31) && rm.x < kOrdInf32 && col != kColNone;
+                        if (good) good = !s.dirty[col] && s.row4col[col] < 0;
+                    }
+                    // an earlier lane of this round wants the same column -> this row conflicts
+                    const unsigned same = __match_any_sync(0xffffffffu, col);
+                    if (good && (same & ((1u << lane) - 1u))) good = false;
+                    const unsigned bad = __ballot_sync(0xffffffffu, !good);   // rows >= n are "bad" too
+                    const int nfast = bad ? (__ffs(bad) - 1) : 32;
+                    if (lane < nfast) {
+                        s.row4col[col] = static_cast<short>(row);
+                        s.col4row[row] = static_cast<int>(col);
+                        s.u[row] = static_cast<double>(unord32(rm.x));
+                    }
+                    cur += nfast;
+                    __syncwarp();
+                    if (nfast < 32) break;
                 }
-                s.ctl[0] = cur;
+                if (lane == 0) s.ctl[0] = cur;
             }
             block_sync<NWARPS>();
             cur = s.ctl[0];
@@ -387,7 +458,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mbx_match_loss_reg_kernel(cons
                     for (int c = 0; c < C; ++c) {
                         const float c32 = cost32(loc[c], g, half_alpha, lc[c], l1[c]);
                         ok = ok && (c32 > -CUDART_INF_F);
-                        c0[c] = c32;
+                        if (!((invalid_mask >> c) & 1u)) c0.set(c, tid + c * T, s.c0, c32);
                         const bool lt = c32 < best32;
                         const unsigned eq = c32 == best32 ? 1u : 0u;
                         best32 = lt ? c32 : best32;
@@ -401,10 +472,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mbx_match_loss_reg_kernel(cons
                         tie = 0u;
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
-                            double sp = static_cast<double>(c0[c]);
+                            const int jc = ((invalid_mask >> c) & 1u) ? 0 : (tid + c * T);
+                            double sp = ((invalid_mask >> c) & 1u) ? INF : static_cast<double>(c0.get(c, jc, s.c0));
                             if ((vnz >> c) & 1u) {
-                                sp = __dsub_rn(sp, v[c]);
-                                spc64[c] = sp;
+                                sp = __dsub_rn(sp, cv.get(c, jc, s.cv));
+                                spc.set(c, jc, s.spc, sp);
                                 dbl |= 1u << c;
                             }
                             const bool lt = sp < best;
@@ -420,14 +492,15 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mbx_match_loss_reg_kernel(cons
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         const float c32 = cost32(loc[c], g, half_alpha, lc[c], l1[c]);
+                        const int jc = ((invalid_mask >> c) & 1u) ? 0 : (tid + c * T);   // in-bounds index
                         const double r =
-                            __dsub_rn(__dsub_rn(__dadd_rn(min_val, static_cast<double>(c32)), ui), v[c]);
+                            __dsub_rn(__dsub_rn(__dadd_rn(min_val, static_cast<double>(c32)), ui), cv.get(c, jc, s.cv));
                         const bool live = !((scmask >> c) & 1u);
-                        const double old = ((dbl >> c) & 1u) ? spc64[c] : static_cast<double>(c0[c]);
+                        const double old = ((dbl >> c) & 1u) ? spc.get(c, jc, s.spc) : static_cast<double>(c0.get(c, jc, s.c0));
                         const bool upd = live && (r < old);
                         if (upd) {
-                            spc64[c] = r;
-                            pm[c] = R;
+                            spc.set(c, jc, s.spc, r);
+                            ptag.set(c, jc, s.pmv, static_cast<short>(R));
                             dbl |= 1u << c;
                             updm |= 1u << c;
                         }
@@ -476,8 +549,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mbx_match_loss_reg_kernel(cons
                     unsigned long long k = ~0ull;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const double sp = ((dbl >> c) & 1u) ? spc64[c] : static_cast<double>(c0[c]);
-                        if (((scmask >> c) & 1u) || !(sp == min_val)) continue;
+                        if ((scmask >> c) & 1u) continue;   // scanned or non-existent column
+                        const double sp = ((dbl >> c) & 1u) ? spc.get(c, tid + c * T, s.spc) : static_cast<double>(c0.get(c, tid + c * T, s.c0));
+                        if (!(sp == min_val)) continue;
                         const int j = tid + c * T;
                         const int pos = replay_pos(j, R, P, s.rm_idx);
                         const bool assigned = (asg >> c) & 1u;
@@ -512,7 +586,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mbx_match_loss_reg_kernel(cons
                         int pmv = 0;
 #pragma unroll
                         for (int c = 0; c < C; ++c)
-                            if (c == cstar && ((updm >> c) & 1u)) pmv = pm[c];
+                            if (c == cstar && ((updm >> c) & 1u)) pmv = ptag.get(c, jstar, s.pmv);
                         scmask |= 1u << cstar;
                         asg |= 1u << cstar;
                         s.u[cur] = min_val;          // u[cur] was 0: 0 + min_val
@@ -537,8 +611,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mbx_match_loss_reg_kernel(cons
 #pragma unroll
                     for (int c = 0; c < C; ++c)
                         if (c == cstar) {
-                            pmv = ((updm >> c) & 1u) ? pm[c] : 0;
-                            arow[c] = r4c_star;
+                            pmv = ((updm >> c) & 1u) ? ptag.get(c, jstar, s.pmv) : 0;
+                            arow.set(c, jstar, s.arow, static_cast<short>(r4c_star));
                         }
                     scmask |= 1u << cstar;
                     s.rm_col[R] = jstar;
@@ -559,19 +633,23 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) mbx_match_loss_reg_kernel(cons
                 const unsigned scanned = scmask & ~invalid_mask;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    if (((scanned >> c) & 1u) && arow[c] >= 0) {
-                        const double sp = ((dbl >> c) & 1u) ? spc64[c] : static_cast<double>(c0[c]);
+                    const int j = tid + c * T;
+                    if (!((scanned >> c) & 1u)) continue;
+                    const int ar = arow.get(c, j, s.arow);
+                    if (ar >= 0) {
+                        const double sp = ((dbl >> c) & 1u) ? spc.get(c, j, s.spc) : static_cast<double>(c0.get(c, j, s.c0));
                         const double delta = __dsub_rn(min_val, sp);
-                        v[c] = __dsub_rn(v[c], delta);
-                        s.u[arow[c]] = __dadd_rn(s.u[arow[c]], delta);
-                        if (v[c] != 0.0) {
+                        const double vn = __dsub_rn(cv.get(c, j, s.cv), delta);
+                        cv.set(c, j, s.cv, vn);
+                        s.u[ar] = __dadd_rn(s.u[ar], delta);
+                        if (vn != 0.0) {
                             vnz |= 1u << c;
                             s.dirty[tid + c * T] = 1;
                             // the precomputed first steps rely on v <= 0; fp rounding could in
                             // principle break that by an ulp: then every later row goes general
-                            if (v[c] > 0.0) s.ctl[1] = 1;
+                            if (vn > 0.0) s.ctl[1] = 1;
                         }
-                        arow[c] = -1;
+                        arow.set(c, j, s.arow, static_cast<short>(-1));
                     }
                 }
             }
@@ -755,13 +833,9 @@ int launch_match_reg(const MatchParams &p, int force_warps, int force_cols, cuda
     if (p.P > 65535 || p.M > 32766) return MBX_E_TOO_LARGE;
     int nwarps = force_warps;
     if (nwarps == 0) {
-        // latency mode (few images: every CTA has an SM to itself) uses wide CTAs; throughput
-        // mode keeps CTAs narrow so several images share an SM.
-        const bool latency = p.B <= 2 * sm_count();
-        if (latency)
-            nwarps = p.P <= 128 ? 2 : (p.P <= 320 ? 4 : (p.P <= 1024 ? 8 : 16));
-        else
-            nwarps = p.P <= 96 ? 1 : (p.P <= 384 ? 2 : (p.P <= 768 ? 4 : 8));
+        // CTA width: enough threads that a thread owns <= 3-4 columns (measured best for both the
+        // few-image, latency-bound case and the many-image, throughput-bound case on B200).
+        nwarps = p.P <= 96 ? 1 : (p.P <= 192 ? 2 : (p.P <= 384 ? 4 : (p.P <= 1024 ? 8 : 16)));
     }
     int cols = force_cols ? force_cols : (p.P + nwarps * 32 - 1) / (nwarps * 32);
     while (!force_warps && cols > 8 && nwarps < 16) {
