@@ -60,6 +60,8 @@ extern "C" {
 #define MBX_FLAG_GENERIC       4u   /* force the generic shared-memory matching kernel (any P) instead
                                        of the register-resident family (tuning / testing) */
 #define MBX_FLAG_WARPS_SHIFT   8    /* bits 8..15: force CTA size in warps (0 = heuristic) */
+#define MBX_FLAG_CLUSTER_SHIFT 24   /* bits 24..27: force the thread-block-cluster size per image of the
+                                       register-resident kernel (1, 2 or 4; 0 = heuristic) */
 #define MBX_FLAG_COLS_SHIFT    16   /* bits 16..23: force columns per thread of the register-resident
                                        kernel (0 = heuristic) */
 

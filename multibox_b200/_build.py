@@ -10,8 +10,10 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["mbx_api.cu", "mbx_match.cu", "mbx_match_reg.cu", "mbx_detect.cu"]
+SOURCES = ["mbx_api.cu", "mbx_match.cu", "mbx_match_reg.cu", "mbx_match_reg_w1.cu", "mbx_match_reg_w2.cu",
+           "mbx_match_reg_w4.cu", "mbx_match_reg_w8.cu", "mbx_match_reg_w16.cu", "mbx_detect.cu"]
 LIB = os.path.join(HERE, "libmultibox_b200.so")
+OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -20,9 +22,8 @@ NVCC_FLAGS = [
     "--fmad=false",            # fp32/fp64 cost arithmetic must not be contracted; FMAs are explicit
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-    "--shared",
-    "-cudart", "shared",
 ]
+LINK_FLAGS = ["--shared", "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def nvcc_path():
@@ -36,24 +37,44 @@ def needs_build():
     if not os.path.isfile(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + \
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] + \
         [os.path.join(HERE, "..", "include", "multibox_b200.h"), os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+def _compile_one(args):
+    src, obj, extra = args
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + ["-c", "-o", obj, src]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return " ".join(cmd) + "\n" + proc.stdout, proc.returncode
+
+
+def build(force=False, verbose=False, extra_flags=(), lib=None):
+    """Compiles every translation unit (in parallel) for sm_100a and links the shared library."""
+    lib = lib or LIB
+    if not force and lib == LIB and not needs_build():
+        return LIB
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = OBJ_DIR + ("_" + "".join(c for c in "".join(extra_flags) if c.isalnum()) if extra_flags else "")
+    os.makedirs(obj_dir, exist_ok=True)
+    jobs = [(os.path.join(CSRC, s), os.path.join(obj_dir, s[:-3] + ".o"), tuple(extra_flags)) for s in SOURCES]
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(_compile_one, jobs))
+    text = "".join(r[0] for r in results)
+    rc = max(r[1] for r in results)
+    if rc == 0:
+        cmd = [nvcc_path()] + LINK_FLAGS + ["-o", lib] + [j[1] for j in jobs]
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        text += " ".join(cmd) + "\n" + proc.stdout
+        rc = proc.returncode
     log = os.path.join(HERE, "csrc", "build.log")
     with open(log, "w") as f:
-        f.write(" ".join(cmd) + "\n" + proc.stdout)
-    if verbose or proc.returncode != 0:
-        print(proc.stdout)
-    if proc.returncode != 0:
+        f.write(text)
+    if verbose or rc != 0:
+        print(text)
+    if rc != 0:
         raise RuntimeError("nvcc failed (see %s)" % log)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

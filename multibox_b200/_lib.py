@@ -21,6 +21,7 @@ FLAG_BOUNDARY = 2
 FLAG_GENERIC = 4
 FLAG_WARPS_SHIFT = 8
 FLAG_COLS_SHIFT = 16
+FLAG_CLUSTER_SHIFT = 24
 STATUS_INVALID_COST = 1
 STATUS_INFEASIBLE = 2
 STATUS_BAD_NUM_GT = 4

@@ -510,9 +510,9 @@ static WsLayout ws_layout(int B) {
     w.ar_seq = o;
     o += 16;
     w.partials = o;
-    o += sizeof(double) * 2 * static_cast<size_t>(B);
+    o += sizeof(double) * 2 * static_cast<size_t>(B) * 4;    // up to 4 CTAs (a cluster) per image
     w.img_matched = o;
-    o += sizeof(int32_t) * static_cast<size_t>(B);
+    o += sizeof(int32_t) * static_cast<size_t>(B) * 4;
     o = align_up(o, 16);
     w.offsets = o;
     o += sizeof(int32_t) * (static_cast<size_t>(B) + 1);
@@ -704,7 +704,8 @@ extern "C" int mbx_match_loss_allreduce(const float *locations, const float *con
     }
     if (!(flags & MBX_FLAG_GENERIC)) {
         // register-resident family first; it declines shapes it has no instantiation for
-        const int rc = launch_match_reg(p, nwarps, ncols, st);
+        const int ncl = static_cast<int>((flags >> MBX_FLAG_CLUSTER_SHIFT) & 0xfu);
+        const int rc = launch_match_reg(p, nwarps, ncols, ncl, st);
         if (rc != MBX_E_TOO_LARGE) return rc;
         if (nwarps > 8) nwarps = 8;
     }

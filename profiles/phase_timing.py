@@ -15,9 +15,7 @@ from multibox_b200 import _build, _lib, synth  # noqa: E402
 out_dir = os.path.join(ROOT, "gpurun_out")
 os.makedirs(out_dir, exist_ok=True)
 so = os.path.join(out_dir, "libmbx_timing.so")
-cmd = [_build.nvcc_path()] + [f for f in _build.NVCC_FLAGS if f not in ("-Xptxas", "-v")] + \
-    ["-DMBX_PHASE_TIMING", "-o", so] + [os.path.join(_build.CSRC, s) for s in _build.SOURCES]
-subprocess.check_call(cmd)
+_build.build(force=True, extra_flags=("-DMBX_PHASE_TIMING",), lib=so)
 _build.LIB = so
 _build.needs_build = lambda: False
 lib = _lib.load()
@@ -62,15 +60,16 @@ if detect_mode:
 for label, d in (("cfg2", synth.make_train_inputs(**synth.TRAIN_CONFIGS["cfg2"])),
                  ("cfg2 full n=20", synth.make_train_inputs(K=5, B=32, M=20, dist="full", seed=5))):
     B, P = d["B"], d["P"]
+    cl = int(os.environ.get("MBX_CLUSTER", "1"))
     for w in ([warps] if warps else [4, 8, 16]):
-        out = {"mask": torch.zeros(max(B * P, B * 16 * 8 * 2 + 64), dtype=torch.int32, device="cuda")}
+        out = {"mask": torch.zeros(max(B * P, B * 16 * 8 * 2 * 4 + 64), dtype=torch.int32, device="cuda")}
         for _ in range(2):
             loss.match_loss_raw(dev(d["locations"]), dev(d["confidences"]).view(B, P), dev(d["gt"]), dev(d["num_gt"]),
-                                dev(d["priors"]), d["alpha"], want_mask=True, warps=w, out=out)
+                                dev(d["priors"]), d["alpha"], want_mask=True, warps=w, cluster=cl, out=out)
         torch.cuda.synchronize()
-        t = out["mask"].cpu().numpy().view(np.int64)[:B * w * 8].reshape(B, w, 8)
-        b = int(np.argmax(d["num_gt"]))      # grid == B here: block b solves image b
-        print("%s warps=%d: image %d (n=%d) per-warp mean cycles by phase" % (label, w, b, d["num_gt"][b]))
+        t = out["mask"].cpu().numpy().view(np.int64)[:B * cl * w * 8].reshape(B, cl * w, 8)
+        b = int(np.argmax(d["num_gt"]))      # grid == B*cl here: cluster b solves image b
+        print("%s warps=%d cluster=%d: image %d (n=%d) per-warp mean cycles by phase" % (label, w, cl, b, d["num_gt"][b]))
         tot = t[b].mean(0)
         for k, nm in enumerate(names):
             print("   %-16s %9.0f  (%.0f per augmentation)" % (nm, tot[k], tot[k] / max(1, d["num_gt"][b])))

@@ -14,12 +14,12 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 
 
-def _run_gpu(d, alpha, logits=False, warps=0, generic=False):
+def _run_gpu(d, alpha, logits=False, warps=0, generic=False, cluster=0):
     conf_in = d["logits"] if logits else d["confidences"]
     out = loss.match_loss_raw(dev(d["locations"]), dev(conf_in).view(d["B"], d["P"]), dev(d["gt"]), dev(d["num_gt"]),
                               dev(d["priors"]), alpha, flags=(1 if logits else 0) | (4 if generic else 0),
                               want_mask=True, want_gt_idx=True,
-                              want_stacked=True, want_grads=True, want_conf_out=logits, warps=warps)
+                              want_stacked=True, want_grads=True, want_conf_out=logits, warps=warps, cluster=cluster)
     torch.cuda.synchronize()
     return {k: v.cpu().numpy() for k, v in out.items()}
 
@@ -54,8 +54,9 @@ def test_loss_cfg2(cuda_device, name, alpha):
 def test_loss_other_shapes(cuda_device, K, B, M, dist):
     d = synth.make_train_inputs(K=K, B=B, M=M, dist=dist, seed=31 + K, edge_cases=True)
     ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], 1000.0)
-    for warps, generic in ((0, False), (16, False), (0, True), (1, True)):
-        _check(d, 1000.0, _run_gpu(d, 1000.0, warps=warps, generic=generic), ref)
+    for warps, generic, cluster in ((0, False, 0), (16, False, 0), (0, True, 0), (1, True, 0), (8, False, 2),
+                                    (8, False, 4), (16, False, 2)):
+        _check(d, 1000.0, _run_gpu(d, 1000.0, warps=warps, generic=generic, cluster=cluster), ref)
 
 
 def test_loss_from_logits(cuda_device):

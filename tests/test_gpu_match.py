@@ -22,11 +22,11 @@ def _sha(*arrays):
     return h.hexdigest()
 
 
-def _gpu_assign(loc, conf, gt, ng, B, alpha, warps=0, cols=0, generic=False):
-    if warps or cols or generic:
+def _gpu_assign(loc, conf, gt, ng, B, alpha, warps=0, cols=0, generic=False, cluster=0):
+    if warps or cols or generic or cluster:
         out = loss.match_loss_raw(dev(loc).view(B, -1, 4), dev(conf).view(B, -1), dev(gt), dev(ng), None, alpha,
                                   flags=2 | (4 if generic else 0), want_mask=True, want_gt_idx=True,
-                                  want_stacked=True, want_grads=False, warps=warps, cols=cols)
+                                  want_stacked=True, want_grads=False, warps=warps, cols=cols, cluster=cluster)
         loss.raise_for_status(out["results"][2].item())
         n = int(out["n_stacked"].item())
         return out["mask"].cpu().numpy(), out["stacked_gt"][:n].cpu().numpy(), out["matched_gt_idx"].cpu().numpy()
@@ -119,6 +119,8 @@ def test_match_vs_c_oracle(cuda_device, K, B, M, dist, alpha):
 VARIANTS = [(1, 0, True), (2, 0, True), (4, 0, True), (8, 0, True),
             (4, 6, False), (4, 8, False), (8, 3, False), (8, 0, False), (16, 2, False), (16, 0, False),
             (2, 0, False)]        # (2, 0): 11 columns per thread -> no instantiation -> generic fallback
+# (warps, cluster): one image per thread-block cluster (distributed shared memory)
+CLUSTER_VARIANTS = [(8, 2), (8, 4), (16, 2)]
 
 
 @pytest.mark.parametrize("warps,cols,generic", VARIANTS)
@@ -128,6 +130,18 @@ def test_match_kernel_variants_agree(cuda_device, warps, cols, generic):
     m0, s0, g0 = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], 12, d["alpha"])
     m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], 12, d["alpha"], warps=warps, cols=cols, generic=generic)
     assert np.array_equal(m, m0) and np.array_equal(gi, g0) and np.array_equal(s, s0)
+
+
+@pytest.mark.parametrize("warps,cluster", CLUSTER_VARIANTS)
+@pytest.mark.parametrize("K,M,dist", [(5, 20, "uniform"), (11, 200, "full")])
+def test_match_cluster_variants_agree(cuda_device, warps, cluster, K, M, dist):
+    B = 9
+    d = synth.make_train_inputs(K=K, B=B, M=M, dist=dist, seed=91 + K, edge_cases=True)
+    loc, conf = boundary_inputs(d)
+    m0, s0, g0 = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], B, d["alpha"])
+    for _ in range(2):
+        m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], B, d["alpha"], warps=warps, cluster=cluster)
+        assert np.array_equal(m, m0) and np.array_equal(gi, g0) and np.array_equal(s, s0)
 
 
 @pytest.mark.parametrize("P,M,warps", [(33, 5, 0), (33, 5, 1), (96, 30, 1), (200, 64, 0), (1024, 8, 0), (2500, 40, 0),
@@ -172,12 +186,13 @@ def test_tie_rule_matches_scipy(cuda_device):
     m1, s1, g1 = np_oracle.compute_assignments(loc.reshape(-1, 4), conf.reshape(-1).copy(), gt, ng, np.int32(B),
                                                np.float32(8.0), return_indices=True)
     assert np.array_equal(m0, m1) and np.array_equal(g0, g1)
-    for warps, cols, generic in [(0, 0, False)] + VARIANTS:
+    for warps, cols, generic, cluster in [(0, 0, False, 0)] + [v + (0,) for v in VARIANTS] + \
+            [(w, 0, False, c) for w, c in CLUSTER_VARIANTS]:
         m, s, gi = _gpu_assign(loc.reshape(-1, 4), conf.reshape(-1), gt, ng, B, 8.0, warps=warps, cols=cols,
-                               generic=generic)
-        assert np.array_equal(m, m0), (warps, cols, generic)
-        assert np.array_equal(gi, g0), (warps, cols, generic)
-        assert np.array_equal(s, s0), (warps, cols, generic)
+                               generic=generic, cluster=cluster)
+        assert np.array_equal(m, m0), (warps, cols, generic, cluster)
+        assert np.array_equal(gi, g0), (warps, cols, generic, cluster)
+        assert np.array_equal(s, s0), (warps, cols, generic, cluster)
 
 
 def test_errors_like_scipy(cuda_device):
@@ -240,15 +255,15 @@ def test_full_size_properties(cuda_device):
         assert np.array_equal(m2[b], m0) and np.array_equal(gi2[b], g0)
 
 
-@pytest.mark.parametrize("warps", [0, 4, 8, 16, 1])
-def test_large_batch_stress(cuda_device, warps):
+@pytest.mark.parametrize("warps,cluster", [(0, 0), (4, 0), (8, 0), (16, 0), (1, 0), (8, 2), (8, 4)])
+def test_large_batch_stress(cuda_device, warps, cluster):
     """Many images per persistent CTA (B=4096, K=5): every image checked against the C oracle
     (fast port), twice, to flush out intra-CTA races."""
     d = synth.make_train_inputs(K=5, B=4096, M=20, dist="uniform", seed=99)
     loc, conf = boundary_inputs(d)
     m0, s0, g0 = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], 4096, d["alpha"])
     for _ in range(2):
-        m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], 4096, d["alpha"], warps=warps)
+        m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], 4096, d["alpha"], warps=warps, cluster=cluster)
         assert np.array_equal(m, m0)
         assert np.array_equal(gi, g0)
         assert np.array_equal(s, s0)
