@@ -216,7 +216,7 @@ struct ColState {
 // thread owns few columns; wide per-thread footprints (C >= 5) trade occupancy for registers.
 template <int NWARPS, int C>
 constexpr int min_blocks_per_sm() {
-    const int warps_per_sm = (C <= 4) ? 16 : ((C <= 6) ? 12 : 8);
+    const int warps_per_sm = (C == 4) ? 24 : ((C <= 3) ? 16 : ((C <= 6) ? 12 : 8));
     return (NWARPS >= warps_per_sm) ? 1 : warps_per_sm / NWARPS;
 }
 
@@ -379,7 +379,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
         // passes THROUGH a column, so all rows can be evaluated up front with no barrier and
         // RB*C independent cost chains per thread.  fp32 keys are exact here (r == C).
         {
-            constexpr int RB = (C <= 2) ? 4 : ((C <= 4) ? 3 : 2);
+            constexpr int RB = (C <= 2) ? 4 : ((C <= 3) ? 3 : 2);
             for (int i0 = 0; i0 < n; i0 += RB) {
                 float4 g[RB];
                 float best[RB];
