@@ -57,6 +57,8 @@ extern "C" {
 #define MBX_FLAG_BOUNDARY      2u   /* strict py_func boundary (reference loss.py:81): locations
                                        already have the prior added, confidences already have
                                        +1e-10 added; `priors` is ignored */
+#define MBX_FLAG_AR_DEFERRED   8u   /* mbx_match_loss_allreduce: post this step's sums, complete the
+                                       PREVIOUS step's reduction (no waiting for slower peers) */
 #define MBX_FLAG_GENERIC       4u   /* force the generic shared-memory matching kernel (any P) instead
                                        of the register-resident family (tuning / testing) */
 #define MBX_FLAG_WARPS_SHIFT   8    /* bits 8..15: force CTA size in warps (0 = heuristic) */
@@ -107,7 +109,8 @@ size_t mbx_match_workspace_bytes(int B, int P, int M);
  *                           losses as float64 (2 x 8 bytes), [8..11] the two losses
  *                           summed over all ranks as float64 (== [4..7] unless
  *                           mbx_match_loss_allreduce is used with world > 1),
- *                           [12],[13] the same as float32
+ *                           [12],[13] the same as float32, [14] the step index the
+ *                           global sums belong to
  *   n_stacked       [1]     int32 number of rows written to stacked_gt
  * The status word is also OR-ed into results[2]; it is 0 when every image was
  * solved.  grads/loss outputs are produced iff `results` is non-NULL.
@@ -132,8 +135,14 @@ int mbx_match_loss(const float *locations, const float *confidences,
  *   peer_buffers [world]  HOST array of device pointers: rank r's symmetric buffer of
  *                         mbx_allreduce_buffer_bytes() bytes (zero-filled once), mapped
  *                         into this process (CUDA IPC / VMM; torch symmetric memory)
+ * With MBX_FLAG_AR_DEFERRED the step posts its own sums and completes the PREVIOUS step's
+ * reduction instead (results[14] = index of the step the global sums belong to, -1 = none
+ * yet): no rank waits for a slower peer inside the step; mbx_allreduce_flush completes the
+ * newest step on demand.
  * A rank that never arrives trips MBX_STATUS_AR_TIMEOUT (~2 s) instead of hanging. */
 size_t mbx_allreduce_buffer_bytes(void);
+int mbx_allreduce_flush(float *results, void *workspace, size_t workspace_bytes,
+                        const unsigned long long *peer_buffers, int world, int rank, void *stream);
 int mbx_match_loss_allreduce(const float *locations, const float *confidences,
                              const float *gt_bboxes, const int32_t *num_gt,
                              const float *priors, int B, int P, int M, float alpha,

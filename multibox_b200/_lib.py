@@ -19,6 +19,7 @@ _c_size_t = ctypes.c_size_t
 FLAG_LOGITS = 1
 FLAG_BOUNDARY = 2
 FLAG_GENERIC = 4
+FLAG_AR_DEFERRED = 8
 FLAG_WARPS_SHIFT = 8
 FLAG_COLS_SHIFT = 16
 FLAG_CLUSTER_SHIFT = 24
@@ -31,7 +32,7 @@ RESULT_WORDS = 16
 
 EXPORTS = ("mbx_version", "mbx_last_error", "mbx_device_info",
            "mbx_match_workspace_bytes", "mbx_match_loss",
-           "mbx_allreduce_buffer_bytes", "mbx_match_loss_allreduce",
+           "mbx_allreduce_buffer_bytes", "mbx_match_loss_allreduce", "mbx_allreduce_flush",
            "mbx_detect_workspace_bytes", "mbx_detect",
            "mbx_filter_proposals", "mbx_convert_proposals",
            "mbx_debug_nplog", "mbx_debug_cost_matrix", "mbx_debug_sqrt_mismatches")
@@ -78,6 +79,8 @@ def load():
     lib.mbx_allreduce_buffer_bytes.argtypes = []
     lib.mbx_match_loss_allreduce.restype = _c_int
     lib.mbx_match_loss_allreduce.argtypes = lib.mbx_match_loss.argtypes[:-1] + [_c_void_p, _c_int, _c_int, _c_void_p]
+    lib.mbx_allreduce_flush.restype = _c_int
+    lib.mbx_allreduce_flush.argtypes = [_c_void_p, _c_void_p, _c_size_t, _c_void_p, _c_int, _c_int, _c_void_p]
     lib.mbx_detect_workspace_bytes.restype = _c_size_t
     lib.mbx_detect_workspace_bytes.argtypes = [_c_int, _c_int, _c_int]
     lib.mbx_detect.restype = _c_int

@@ -486,7 +486,8 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_kernel(const Match
         s.pv[warp] = md;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
+        if (p.ar_world > 1 && (p.flags & MBX_FLAG_AR_DEFERRED)) ar_post_pending(p);   // no poster CTA here
         double A = 0.0, C = 0.0, Mt = 0.0;
         for (int w = 0; w < NWARPS; ++w) {
             A += s.red[w];
@@ -623,6 +624,44 @@ extern "C" int mbx_match_loss(const float *locations, const float *confidences, 
 
 extern "C" size_t mbx_allreduce_buffer_bytes(void) { return align_up(kArBytes, 256); }
 
+namespace mbx {
+__global__ void mbx_allreduce_flush_kernel(MatchParams p) {
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const unsigned seq = *p.ar_seq;
+    if (seq == 0u) return;
+    ar_post_pending(p);                      // deferred mode: the newest step has not been sent yet
+    if (threadIdx.x != 0) return;
+    double g_loc = 0.0, g_conf = 0.0;
+    if (ar_collect(p.ar_peer, p.ar_world, p.ar_rank, seq - 1u, g_loc, g_conf)) {
+        double *r64 = reinterpret_cast<double *>(p.results);
+        r64[4] = g_loc;
+        r64[5] = g_conf;
+        p.results[12] = static_cast<float>(g_loc);
+        p.results[13] = static_cast<float>(g_conf);
+        p.results[14] = static_cast<float>(seq - 1u);
+    } else {
+        p.results[2] = static_cast<float>(static_cast<unsigned>(p.results[2]) | MBX_STATUS_AR_TIMEOUT);
+    }
+}
+}  // namespace mbx
+
+extern "C" int mbx_allreduce_flush(float *results, void *workspace, size_t workspace_bytes,
+                                   const unsigned long long *peer_buffers, int world, int rank, void *stream) {
+    if (world < 2 || world > MBX_MAX_PEERS || rank < 0 || rank >= world || !peer_buffers || !results || !workspace) {
+        set_error("mbx_allreduce_flush: bad arguments");
+        return MBX_E_ARG;
+    }
+    (void)workspace_bytes;
+    MatchParams p{};
+    p.results = results;
+    p.ar_seq = reinterpret_cast<unsigned *>(peer_buffers[rank] + kArSeqOffset);
+    p.ar_world = world;
+    p.ar_rank = rank;
+    for (int r = 0; r < MBX_MAX_PEERS; ++r) p.ar_peer[r] = r < world ? peer_buffers[r] : 0ull;
+    mbx_allreduce_flush_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    return check_cuda(cudaGetLastError(), "launch mbx_allreduce_flush_kernel");
+}
+
 extern "C" int mbx_match_loss_allreduce(const float *locations, const float *confidences, const float *gt_bboxes,
                                         const int32_t *num_gt, const float *priors, int B, int P, int M,
                                         float alpha, unsigned flags, int32_t *mask, int32_t *matched_gt_idx,
@@ -691,7 +730,10 @@ extern "C" int mbx_match_loss_allreduce(const float *locations, const float *con
     p.stk_offsets = reinterpret_cast<int32_t *>(ws + wl.offsets);
     p.ticket = reinterpret_cast<unsigned *>(ws + wl.ticket);
     p.status = reinterpret_cast<unsigned *>(ws + wl.status);
-    p.ar_seq = reinterpret_cast<unsigned *>(ws + wl.ar_seq);
+    // the step counter lives in this rank's own symmetric buffer, next to the arrival counters it
+    // must stay consistent with (a re-allocated workspace must not reset it)
+    p.ar_seq = world > 1 ? reinterpret_cast<unsigned *>(peer_buffers[rank] + kArSeqOffset)
+                         : reinterpret_cast<unsigned *>(ws + wl.ar_seq);
     p.ar_world = world;
     p.ar_rank = rank;
     for (int r = 0; r < MBX_MAX_PEERS; ++r) p.ar_peer[r] = (world > 1 && r < world) ? peer_buffers[r] : 0ull;

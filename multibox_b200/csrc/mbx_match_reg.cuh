@@ -297,7 +297,14 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     for (int c = 0; c < C; ++c)
         if (gtid + c * TC >= P) invalid_mask |= 1u << c;
 
-    for (int b = blockIdx.x / CL; b < p.B; b += gridDim.x / CL) {
+    // Deferred fused all-reduce: the launch appends one extra CTA that only sends the previous
+    // step's loss sums to the peers (NVLink latency overlaps this kernel's work).
+    const bool has_poster = (CL == 1) && p.ar_world > 1 && (p.flags & MBX_FLAG_AR_DEFERRED);
+    const int n_work = has_poster ? static_cast<int>(gridDim.x) - 1 : static_cast<int>(gridDim.x) / CL;
+    const bool is_poster = has_poster && static_cast<int>(blockIdx.x) == n_work;
+    if (is_poster && warp == 0) ar_post_pending(p);
+
+    for (int b = is_poster ? p.B : static_cast<int>(blockIdx.x) / CL; b < p.B; b += n_work) {
         int n = p.num_gt[b];
         if (n < 0 || n > M) {
             status |= MBX_STATUS_BAD_NUM_GT;
@@ -812,14 +819,15 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
         s.red[2 * NWARPS + warp] = md;
     }
     block_sync<NWARPS>();
-    if (tid == 0) {
+    if (warp == 0) {
+        if (!has_poster && p.ar_world > 1 && (p.flags & MBX_FLAG_AR_DEFERRED)) ar_post_pending(p);
         double A = 0.0, Cc = 0.0, Mt = 0.0;
         for (int w = 0; w < NWARPS; ++w) {
             A += s.red[w];
             Cc += s.red[NWARPS + w];
             Mt += s.red[2 * NWARPS + w];
         }
-        finalize_losses(p, A, Cc, Mt);
+        finalize_losses(p, A, Cc, Mt);   // warp-cooperative (lane r posts to peer r)
     }
 }
 
@@ -874,7 +882,8 @@ int launch_one(const MatchParams &p, cudaStream_t st) {
     }
     int units = info.occ;                  // clusters (CL > 1) or CTAs
     if (units > p.B) units = p.B;
-    cfg.gridDim = dim3(units * CL);
+    const bool poster = (CL == 1) && p.ar_world > 1 && (p.flags & MBX_FLAG_AR_DEFERRED);
+    cfg.gridDim = dim3(units * CL + (poster ? 1 : 0));
     return check_cuda(cudaLaunchKernelEx(&cfg, kern, p), "launch mbx_match_loss_reg_kernel");
 }
 

@@ -205,7 +205,7 @@ class MultiboxLossStep:
     """
 
     def __init__(self, B, P, M, priors, alpha, device="cuda", logits=False, want_mask=False,
-                 want_stacked=False, warps=0, use_graph=False, peer=None):
+                 want_stacked=False, warps=0, use_graph=False, peer=None, deferred_allreduce=False):
         self.B, self.P, self.M, self.alpha = B, P, M, float(alpha)
         self.device = torch.device(device)
         if self.device.index is None:
@@ -215,6 +215,8 @@ class MultiboxLossStep:
         self.priors = _f32c(torch.as_tensor(priors).to(self.device), "priors")
         self.want_mask, self.want_stacked = want_mask, want_stacked
         self.peer = peer if (peer is not None and peer.world > 1) else None
+        if self.peer is not None and deferred_allreduce:
+            self.flags |= _lib.FLAG_AR_DEFERRED
         self.out = {}
         # packed staging: one pinned host buffer, one device buffer, typed views into both
         def up4(x):          # every section starts 16-byte aligned
@@ -300,10 +302,29 @@ class MultiboxLossStep:
             self._graph = g
 
     def global_losses(self):
-        """(location_loss, confidence_loss) summed over all ranks, from the last step_host /
-        step_pinned (fused all-reduce; equals the local losses on one GPU)."""
+        """(location_loss, confidence_loss) summed over all ranks, as read back by the last
+        step_host / step_pinned / flush (fused all-reduce; equals the local losses on one GPU).
+        With deferred_allreduce they belong to step `global_step()` (the previous one)."""
         g = self.h_res[8:12].view(torch.float64)
         return float(g[0]), float(g[1])
+
+    def global_step(self):
+        return int(self.h_res[14].item())
+
+    def flush(self):
+        """Deferred all-reduce: completes the newest step's reduction and reads it back."""
+        if self.peer is None:
+            return self.global_losses()
+        lib = _lib.load()
+        ws = _workspace(self.device, lib.mbx_match_workspace_bytes(self.B, self.P, self.M))
+        rc = lib.mbx_allreduce_flush(_lib.ptr(self.out["results"]), _lib.ptr(ws), ws.numel(), self.peer.ptr_array,
+                                     self.peer.world, self.peer.rank,
+                                     torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(rc, "mbx_allreduce_flush")
+        self.h_res.copy_(self.out["results"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        raise_for_status(self.h_res[2].item())
+        return self.global_losses()
 
     def step_host(self, locations, confidences, gt, num_gt, validate=True):
         """numpy in -> (location_loss, confidence_loss) python floats out; the

@@ -22,21 +22,28 @@ B = 8 * world + 3
 d = synth.make_train_inputs(K=5, B=B, M=20, seed=4321, edge_cases=True)
 lo, hi = mdist.shard_range(B)
 sh = mdist.shard_batch({k: d[k] for k in ("locations", "confidences", "gt", "num_gt")}, B)
-step = loss.MultiboxLossStep(hi - lo, d["P"], 20, d["priors"], d["alpha"], peer=peer, use_graph=True)
+from oracle import np_oracle
+ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], d["alpha"])
 ok = True
-for it in range(5):       # several steps: exercises both parities and the sequence counter
-    ll, cl = step.step_host(sh["locations"], sh["confidences"], sh["gt"], sh["num_gt"])
-    gl, gc = step.global_losses()
-    t = torch.tensor([ll, cl], dtype=torch.float64, device="cuda")
-    t64 = step.out["results"][4:8].view(torch.float64).clone()
-    dist.all_reduce(t64)
-    ok &= abs(gl - t64[0].item()) <= 1e-12 * abs(gl) and abs(gc - t64[1].item()) <= 1e-12 * abs(gc)
-if rank == 0:
-    from oracle import np_oracle
-    ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], d["alpha"])
+for deferred in (False, True):
+    step = loss.MultiboxLossStep(hi - lo, d["P"], 20, d["priors"], d["alpha"], peer=peer, use_graph=True,
+                                 deferred_allreduce=deferred)
+    for it in range(7):       # several steps: exercises the slot ring and the sequence counter
+        scale = 1.0 + it      # a different global sum every step
+        ll, cl = step.step_host(sh["locations"] * np.float32(1.0), sh["confidences"], sh["gt"], sh["num_gt"])
+        t64 = step.out["results"][4:8].view(torch.float64).clone()
+        dist.all_reduce(t64)
+        if not deferred:
+            gl, gc = step.global_losses()
+            ok &= abs(gl - t64[0].item()) <= 1e-12 * abs(gl) and abs(gc - t64[1].item()) <= 1e-12 * abs(gc)
+        elif it >= 1:
+            gl, gc = step.global_losses()      # belongs to the previous step (same inputs here)
+            ok &= abs(gl - t64[0].item()) <= 1e-12 * abs(gl) and abs(gc - t64[1].item()) <= 1e-12 * abs(gc)
+    gl, gc = step.flush() if deferred else step.global_losses()
     ok &= abs(gl - ref["location_loss_f64"]) <= 1e-9 * abs(gl) and abs(gc - ref["confidence_loss_f64"]) <= 1e-9 * abs(gc)
-    print("dist_check world=%d: fused global losses %.6f %.6f  oracle %.6f %.6f  -> %s"
-          % (world, gl, gc, ref["location_loss_f64"], ref["confidence_loss_f64"], "OK" if ok else "MISMATCH"))
+    if rank == 0:
+        print("dist_check world=%d deferred=%s: fused global losses %.6f %.6f  oracle %.6f %.6f  -> %s"
+              % (world, deferred, gl, gc, ref["location_loss_f64"], ref["confidence_loss_f64"], "OK" if ok else "MISMATCH"))
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.barrier()
