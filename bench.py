@@ -46,7 +46,8 @@ def traffic_from_profiles(kernel):
     """dram bytes per launch from the committed ncu summary, if any."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(kernel)
+            e = json.load(f).get(kernel)
+            return e["dram_bytes_per_launch"] if isinstance(e, dict) else e
     except Exception:
         return None
 
@@ -506,6 +507,7 @@ def main():
             "min_cost_evals_per_s": world * evals * tsteps / tsec,
             "roofline": {"bound": "hbm", "achieved": tach, "peak": peak, "unit": "GB/s", "frac": tach / peak,
                          "kernel_ms": tk, "bytes_per_launch": tbytes,
+                         "traffic": traffic_from_profiles("mbx_match_loss_kernel_cfg5shape"),
                          "note": "assignment solver: >= n*P cost evaluations per image (fp32 cost + fp64 duals), "
                                  "compute/latency-bound, reported against the HBM figure as the contract asks"},
         }
