@@ -59,6 +59,8 @@ extern "C" {
                                        +1e-10 added; `priors` is ignored */
 #define MBX_FLAG_AR_DEFERRED   8u   /* mbx_match_loss_allreduce: post this step's sums, complete the
                                        PREVIOUS step's reduction (no waiting for slower peers) */
+#define MBX_FLAG_STATIC        16u  /* keep the static image -> CTA assignment even when the batch exceeds
+                                       the resident CTAs (default then: heavy-first dynamic scheduling) */
 #define MBX_FLAG_GENERIC       4u   /* force the generic shared-memory matching kernel (any P) instead
                                        of the register-resident family (tuning / testing) */
 #define MBX_FLAG_WARPS_SHIFT   8    /* bits 8..15: force CTA size in warps (0 = heuristic) */

@@ -15,6 +15,8 @@
 //   eval.py:146-167    decode / clip / full sort / top-100             -> same kernel, no filter
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "mbx_common.cuh"
 
 // Optional phase timing (profiles/phase_timing.py --detect builds with -DMBX_PHASE_TIMING).
@@ -57,18 +59,26 @@ __device__ __forceinline__ float clip01(float x) { return x < 0.0f ? 0.0f : (x >
 
 // fp32 IoU test exactly as oracle/np_oracle.greedy_nms (and torchvision's CPU nms) decides it:
 //   fl(inter / ((area_a + area_b) - inter)) > thr.
-// iou_fast forms the quotient with the fast reciprocal (<= 2 ulp off) and reports `near` when it
-// lands within a few ulp of the threshold; only those (rare) pairs are re-decided with the IEEE
-// division (iou_exact), so the final decision is always the exact one without a branch in the
-// common path.
+// iou_fast decides WITHOUT a division: with den > 0, x = inter/den and t = fl(thr*den),
+//   inter > t*(1+2^-20)  =>  x > thr*(1+2^-21) > nextafter(thr)  =>  fl(x) > thr     (rounding is monotone)
+//   inter < t*(1-2^-20)  =>  x < thr                             =>  fl(x) <= thr
+// so only pairs with |inter - t| <= 2^-20*t (or a denominator that is not a comfortably normal
+// positive number: tiny, inf) are `near`; those (rare) pairs are re-decided with the
+// IEEE division (iou_exact), and the final decision is always the exact one.  The caller must
+// route EVERY pair through iou_exact when thr itself is outside [2^-20, 2^20] (thr_ok below).
+// The claim is also checked numerically on the host by tests/test_nms_decision_math.py.
 __device__ __forceinline__ bool iou_fast(float4 a, float area_a, float4 b, float area_b, float thr, bool &near) {
     const float w = fmaxf(0.0f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
     const float h = fmaxf(0.0f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
     const float inter = __fmul_rn(w, h);
     const float den = __fsub_rn(__fadd_rn(area_a, area_b), inter);
-    const float q = __fdividef(inter, den);
-    near = fabsf(q - thr) <= 1e-6f * fabsf(thr);
-    return q > thr;
+    const float t = __fmul_rn(thr, den);
+    const float d = __fsub_rn(inter, t);
+    // den <= 0 needs no second look either (inter >= 0, thr > 0): den < 0 (a box with x2 < x1 -- the
+    // reference applies no validity fix-up, detect.py:412-413) gives a quotient <= 0, never > thr;
+    // den == 0 gives t = 0, d = inter, and inter/0 > thr <=> inter > 0.
+    near = (den > 0.0f) && (!(den >= 1e-20f) || !(fabsf(d) > __fmul_rn(9.5367431640625e-07f, t)));
+    return (d > 0.0f) && (den >= 0.0f);
 }
 __device__ __noinline__ bool iou_exact(float4 a, float area_a, float4 b, float area_b, float thr) {
     const float w = fmaxf(0.0f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
@@ -90,7 +100,8 @@ struct DSmem {
     unsigned long long *keys, *ckeys;
     int *hist;
     float *sarea;
-    uint32_t *nmask, *keepw;
+    uint32_t *diag, *remw, *keepw;
+    int *klist;
     int *keeppre, *cnt;
     uint64_t *bar;
 };
@@ -108,15 +119,17 @@ __host__ __device__ inline size_t dcarve(DSmem *s, unsigned char *base, int P, i
     };
     size_t o_pri = take(sizeof(float4) * P, 16);
     size_t o_box = take(sizeof(float4) * P, 16);
-    size_t o_sbox = take(nms ? sizeof(float4) * k_max : 0, 16);
+    size_t o_sbox = take(nms ? sizeof(float4) * (W * 32) : 0, 16);   // padded to whole 32-row blocks
     size_t o_keys = take(sizeof(unsigned long long) * n2, 8);
     size_t o_ckeys = take(sizeof(unsigned long long) * n2, 8);
     size_t o_bar = take(8, 8);
     size_t o_hist = take(sizeof(int) * kBins, 4);
-    size_t o_area = take(nms ? sizeof(float) * k_max : 0, 4);
-    size_t o_nm = take(nms ? sizeof(uint32_t) * static_cast<size_t>(k_max) * W : 0, 4);
+    size_t o_area = take(nms ? sizeof(float) * (W * 32) : 0, 4);
+    size_t o_nm = take(nms ? sizeof(uint32_t) * (W * 32) : 0, 4);     // diag[i]: whom box i suppresses inside its chunk
+    size_t o_tc = take(sizeof(uint32_t) * 32, 4);                      // remw[w]: boxes of chunk w removed by earlier chunks
     size_t o_kw = take(sizeof(uint32_t) * 32, 4);
     size_t o_kp = take(sizeof(int) * 33, 4);
+    size_t o_kl = take(sizeof(int) * 32, 4);
     size_t o_cnt = take(sizeof(int) * 4, 4);
     if (s) {
         s->priors = reinterpret_cast<float4 *>(base + o_pri);
@@ -127,9 +140,11 @@ __host__ __device__ inline size_t dcarve(DSmem *s, unsigned char *base, int P, i
         s->hist = reinterpret_cast<int *>(base + o_hist);
         s->bar = reinterpret_cast<uint64_t *>(base + o_bar);
         s->sarea = reinterpret_cast<float *>(base + o_area);
-        s->nmask = reinterpret_cast<uint32_t *>(base + o_nm);
+        s->diag = reinterpret_cast<uint32_t *>(base + o_nm);
         s->keepw = reinterpret_cast<uint32_t *>(base + o_kw);
+        s->remw = reinterpret_cast<uint32_t *>(base + o_tc);
         s->keeppre = reinterpret_cast<int *>(base + o_kp);
+        s->klist = reinterpret_cast<int *>(base + o_kl);
         s->cnt = reinterpret_cast<int *>(base + o_cnt);
     }
     return dalign(o, 16);
@@ -369,97 +384,160 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
         MBX_DT(1);   // select + sort
         const int kk = target;
         int count = kk;
-        // ---- greedy NMS over the kk sorted survivors (extension)
+        // ---- greedy NMS over the kk sorted survivors (extension), chunk-serial bitmask formulation.
+        // The survivors are cut into chunks of 32 in score order; lanes are boxes of a chunk.
+        //   phase B  every chunk's OWN 32x32 triangle (does box i suppress a later box j of the same
+        //            chunk?) is evaluated up front by all warps: one ballot per row -> diag[i];
+        //   phase C  chunk by chunk: warp 0 resolves the chunk serially from diag and the bits earlier
+        //            chunks left in remw[c] (32 shuffles + a 32-step register chain), then the warps
+        //            share the ONLY pairwise work greedy NMS really needs -- the chunk's KEPT boxes
+        //            against the boxes of the later chunks -- OR-ing their verdicts into remw[w]; two
+        //            barriers per chunk.
+        // Suppressed boxes are never used as suppressors, so about half of the upper triangle of
+        // the pair matrix is never evaluated, and nothing is ever stored per pair.
         if (nms) {
             const int W = (kk + 31) >> 5;
-            for (int t = tid; t < kk; t += T) {
-                const float4 bx = s.box[static_cast<unsigned>(s.ckeys[t] & 0xffffffffu)];
+            // a threshold outside [2^-20, 2^20] voids iou_fast's error analysis: decide every pair exactly
+            const bool thr_ok = p.nms_iou >= 9.5367431640625e-07f && p.nms_iou <= 1048576.0f;
+            for (int t = tid; t < (W << 5); t += T) {   // rows past kk: zero boxes (never kept, never dead)
+                float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t < kk) bx = s.box[static_cast<unsigned>(s.ckeys[t] & 0xffffffffu)];
                 s.sbox[t] = bx;
                 s.sarea[t] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
             }
+            if (tid < 32) s.remw[tid] = 0u;
             __syncthreads();
-            // suppression matrix: bit j of nmask[i][w] <=> j = 32w+bit > i and IoU(i, j) > thr.
-            // Work unit = (column word w, block of 32 rows rb <= w): the lanes keep their column's
-            // box in registers, rows are broadcast from shared memory, one ballot per row.
-            const int WS = (KM + 31) >> 5;
-            const int units = W * (W + 1) / 2;
-            for (int t = warp; t < units; t += NWARPS) {
-                int w = 0;
-                while ((w + 1) * (w + 2) / 2 <= t) ++w;
-                const int rb = t - w * (w + 1) / 2;
-                const int jj = (w << 5) + lane;
+            constexpr int RU = 8;   // rows per unit of phase B: RU independent IoU decisions per lane
+            for (int t = warp; t < W * (32 / RU); t += NWARPS) {
+                const int c = t / (32 / RU), ib = (t % (32 / RU)) * RU;
+                const int i0 = (c << 5) + ib;
+                if (i0 >= kk) continue;
+                const int jj = (c << 5) + lane;
                 const bool jvalid = jj < kk;
-                const float4 bj = s.sbox[jvalid ? jj : 0];
-                const float aj = s.sarea[jvalid ? jj : 0];
-                const int i0 = rb << 5;
-                constexpr int RU = 8;   // rows per batch: RU independent IoU chains per lane
-                for (int ib = 0; ib < 32; ib += RU) {
-                    bool sup[RU], near[RU];
+                const float4 bj = s.sbox[jj];
+                const float aj = s.sarea[jj];
+                const float4 *rbox = s.sbox + i0;
+                const float *rarea = s.sarea + i0;
+                unsigned bal[RU];
+                bool any_near = !thr_ok && jvalid;
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    const bool act = jvalid && lane > ib + u;   // j > i (and so i < kk, since j < kk)
+                    bool nr;
+                    const bool sp = iou_fast(rbox[u], rarea[u], bj, aj, p.nms_iou, nr);
+                    bal[u] = __ballot_sync(0xffffffffu, sp && act);
+                    any_near = any_near || (nr && act);
+                }
+                if (__any_sync(0xffffffffu, any_near)) {   // rare: a quotient within ulps of thr
 #pragma unroll
                     for (int u = 0; u < RU; ++u) {
-                        const int i = i0 + ib + u;
-                        const int ic = i < kk ? i : 0;
-                        const bool act = jvalid && jj > i && i < kk;
+                        const bool act = jvalid && lane > ib + u;
                         bool nr;
-                        const bool sp = iou_fast(s.sbox[ic], s.sarea[ic], bj, aj, p.nms_iou, nr);
-                        sup[u] = sp && act;
-                        near[u] = nr && act;
-                    }
-                    bool any_near = false;
-#pragma unroll
-                    for (int u = 0; u < RU; ++u) any_near |= near[u];
-                    if (__any_sync(0xffffffffu, any_near)) {   // rare: a quotient within ulps of thr
-#pragma unroll
-                        for (int u = 0; u < RU; ++u) {
-                            const int i = i0 + ib + u;
-                            if (near[u]) sup[u] = iou_exact(s.sbox[i], s.sarea[i], bj, aj, p.nms_iou);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < RU; ++u) {
-                        const int i = i0 + ib + u;
-                        const unsigned bal = __ballot_sync(0xffffffffu, sup[u]);
-                        if (lane == u && i < kk) s.nmask[i * WS + w] = bal;
+                        bool sp = iou_fast(rbox[u], rarea[u], bj, aj, p.nms_iou, nr);
+                        if (act && (nr || !thr_ok)) sp = iou_exact(rbox[u], rarea[u], bj, aj, p.nms_iou);
+                        bal[u] = __ballot_sync(0xffffffffu, sp && act);
                     }
                 }
+                unsigned mine = 0u;
+#pragma unroll
+                for (int u = 0; u < RU; ++u) mine = (lane == u) ? bal[u] : mine;
+                if (lane < RU) s.diag[i0 + lane] = mine;   // rows >= kk: all-zero ballots
             }
             __syncthreads();
-            MBX_DT(2);   // suppression matrix
-            if (warp == 0) {
-                // greedy sweep in score order, one 32-box chunk at a time.  Lane w owns the
-                // "suppressed by an earlier kept box" word of chunk w.  Inside a chunk the kept set
-                // is the unique fixed point of  kept_i = cand_i & !exists kept_j (j<i) suppressing i,
-                // reached by iterating from kept = cand (bit i is final after i+1 rounds).
-                unsigned rem = 0u, keptw = 0u;
-                for (int c = 0; c < W; ++c) {
-                    const int row = (c << 5) + lane;
-                    const unsigned d = (row < kk) ? s.nmask[row * WS + c] : 0u;   // whom box `row` suppresses in this chunk
-                    unsigned tcol = 0u;                                           // who suppresses box `row` in this chunk
+            MBX_DT(2);   // diagonal triangles
+            unsigned keptw = 0u;   // warp 0, lane c: kept mask of chunk c
+            for (int c = 0; c < W; ++c) {
+                // ---- serial resolve of chunk c by warp 0: 32 shuffles + a 32-step register chain
+                if (warp == 0) {
+                    const unsigned d = s.diag[(c << 5) + lane];
+                    const int left = kk - (c << 5);
+                    const unsigned valid = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+                    unsigned removed = s.remw[c] | ~valid;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const unsigned bal = __ballot_sync(0xffffffffu, (d >> i) & 1u);
-                        if (lane == i) tcol = bal;
+                        const unsigned di = __shfl_sync(0xffffffffu, d, i);   // whom box i suppresses (bits > i)
+                        if (!(removed & (1u << i))) removed |= di;
                     }
-                    const unsigned remc = __shfl_sync(0xffffffffu, rem, c);
-                    const unsigned valid = (kk - (c << 5) >= 32) ? 0xffffffffu : ((1u << (kk - (c << 5))) - 1u);
-                    const unsigned cand = ~remc & valid;
-                    unsigned kept = cand;
-                    for (int it = 0; it < 32; ++it) {
-                        const bool dead = (tcol & kept) != 0u;      // tcol only has bits j < lane
-                        const unsigned nk = __ballot_sync(0xffffffffu, !dead) & cand;
-                        if (nk == kept) break;
-                        kept = nk;
-                    }
+                    const unsigned kept = ~removed;
                     if (lane == c) keptw = kept;
-                    // propagate the kept boxes' suppression to the later chunks: lanes = rows of this
-                    // chunk, one OR-reduction per later word (lane w keeps word w)
-                    const bool my_kept = (kept >> lane) & 1u;
-                    for (int w = c + 1; w < W; ++w) {
-                        const unsigned m = my_kept ? s.nmask[row * WS + w] : 0u;
-                        const unsigned orw = __reduce_or_sync(0xffffffffu, m);
-                        if (lane == w) rem |= orw;
-                    }
+                    const int nk = __popc(kept);
+                    // klist[l] = row of the l-th kept box of the chunk
+                    s.klist[lane] = lane < nk ? (c << 5) + static_cast<int>(__fns(kept, 0, lane + 1)) : -1;
+                    if (lane == 0) s.cnt[3] = nk;
                 }
+                const int nwords = W - 1 - c;
+                if (nwords == 0) break;
+                __syncthreads();
+                // ---- the kept boxes of chunk c against the later chunks.  A lane owns NC boxes (one in
+                // each of NC later chunks: the row broadcast and its bookkeeping are shared by NC
+                // decisions); the warps split the work by (group of NC chunks, slice of the kept rows)
+                // and OR one ballot per chunk into remw[].
+                const int nkept = s.cnt[3];
+                const int myrow = s.klist[lane];
+                auto cross = [&](auto nc_tag) {
+                    constexpr int NC = decltype(nc_tag)::value;
+                    const int CG = (nwords + NC - 1) / NC;
+                    const int RS = CG >= NWARPS ? 1 : NWARPS / CG;
+                    for (int gg = warp; gg < CG * RS; gg += NWARPS) {
+                        const int g = gg % CG, r = gg / CG;
+                        float4 bj[NC];
+                        float aj[NC];
+                        bool jvalid[NC], dead[NC];
+                        bool any_near = false;
+#pragma unroll
+                        for (int k = 0; k < NC; ++k) {
+                            const int w = c + 1 + g * NC + k;
+                            const int jj = (w << 5) + lane;
+                            jvalid[k] = w < W && jj < kk;
+                            bj[k] = s.sbox[jvalid[k] ? jj : 0];
+                            aj[k] = s.sarea[jvalid[k] ? jj : 0];
+                            dead[k] = false;
+                            any_near = any_near || (!thr_ok && jvalid[k]);
+                        }
+                        for (int o = r; o < nkept; o += 2 * RS) {
+                            const int i0 = __shfl_sync(0xffffffffu, myrow, o);
+                            const bool on1 = o + RS < nkept;
+                            const int i1 = on1 ? __shfl_sync(0xffffffffu, myrow, (o + RS) & 31) : i0;
+                            const float4 b0 = s.sbox[i0], b1 = s.sbox[i1];
+                            const float a0 = s.sarea[i0], a1 = s.sarea[i1];
+#pragma unroll
+                            for (int k = 0; k < NC; ++k) {
+                                bool n0, n1;
+                                const bool s0 = iou_fast(b0, a0, bj[k], aj[k], p.nms_iou, n0);
+                                const bool s1 = iou_fast(b1, a1, bj[k], aj[k], p.nms_iou, n1);
+                                dead[k] = dead[k] || s0 || s1;      // (i1 == i0 when the second row is off)
+                                any_near = any_near || ((n0 || n1) && jvalid[k]);
+                            }
+                        }
+                        if (__any_sync(0xffffffffu, any_near)) {   // rare: redo my rows with the IEEE division
+                            for (int k = 0; k < NC; ++k) dead[k] = false;
+                            for (int o = r; o < nkept; o += RS) {
+                                const int i = __shfl_sync(0xffffffffu, myrow, o);
+#pragma unroll
+                                for (int k = 0; k < NC; ++k) {
+                                    bool nr;
+                                    bool sp = iou_fast(s.sbox[i], s.sarea[i], bj[k], aj[k], p.nms_iou, nr);
+                                    if (nr || !thr_ok) sp = iou_exact(s.sbox[i], s.sarea[i], bj[k], aj[k], p.nms_iou);
+                                    dead[k] = dead[k] || sp;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < NC; ++k) {
+                            const unsigned m = __ballot_sync(0xffffffffu, dead[k] && jvalid[k]);
+                            if (lane == 0 && m) atomicOr(&s.remw[c + 1 + g * NC + k], m);
+                        }
+                    }
+                };
+                if (nwords >= 3)
+                    cross(std::integral_constant<int, 4>{});
+                else if (nwords == 2)
+                    cross(std::integral_constant<int, 2>{});
+                else
+                    cross(std::integral_constant<int, 1>{});
+                __syncthreads();   // remw[c+1..] complete before the next chunk is resolved
+            }
+            if (warp == 0) {
                 // exclusive prefix of kept counts per word
                 const int c = __popc(keptw);
                 int inc = c;
@@ -474,7 +552,7 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
             }
             __syncthreads();
             count = s.keeppre[32];
-            MBX_DT(3);   // sweep (+ wait)
+            MBX_DT(3);   // chunk-serial resolve + cross-chunk suppression
         }
         // ---- store (convert_proposals in float64)
         double sx = 1.0, sy = 1.0, ox = 0.0, oy = 0.0;

@@ -304,7 +304,16 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     const bool is_poster = has_poster && static_cast<int>(blockIdx.x) == n_work;
     if (is_poster && warp == 0) ar_post_pending(p);
 
-    for (int b = is_poster ? p.B : static_cast<int>(blockIdx.x) / CL; b < p.B; b += n_work) {
+    // Image scheduling.  Static (image = CTA index, stride = resident CTAs) when every image has
+    // its own CTA; otherwise DYNAMIC over the heavy-first order built by mbx_order_kernel: the
+    // first wave takes positions 0..n_work-1, later positions are claimed from a global counter.
+    // Thread 0 issues the claim when an image starts and reads it when the image is done, so the
+    // L2 round trip of the atomic is off the critical path.
+    const bool dyn = (CL == 1) && p.dynamic != 0;
+    for (int q = is_poster ? p.B : static_cast<int>(blockIdx.x) / CL; q < p.B;) {
+        const int b = dyn ? p.order[q] : q;
+        unsigned claim = 0u;
+        if (dyn && tid == 0) claim = atomicAdd(p.queue, 1u);
         int n = p.num_gt[b];
         if (n < 0 || n > M) {
             status |= MBX_STATUS_BAD_NUM_GT;
@@ -781,7 +790,9 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             p.partials[2 * (b * CL + crank) + 1] = cc;
             p.img_matched[b * CL + crank] = m;
         }
+        if (dyn && tid == 0) s.ctl[2] = n_work + static_cast<int>(claim);
         block_sync<NWARPS>();   // shared state is reused by the next image
+        q = dyn ? s.ctl[2] : q + n_work;
     }
 
     if (status) atomicOr(p.status, status);
@@ -884,7 +895,13 @@ int launch_one(const MatchParams &p, cudaStream_t st) {
     if (units > p.B) units = p.B;
     const bool poster = (CL == 1) && p.ar_world > 1 && (p.flags & MBX_FLAG_AR_DEFERRED);
     cfg.gridDim = dim3(units * CL + (poster ? 1 : 0));
-    return check_cuda(cudaLaunchKernelEx(&cfg, kern, p), "launch mbx_match_loss_reg_kernel");
+    MatchParams pp = p;
+    if (CL == 1 && p.B > units && !(p.flags & MBX_FLAG_STATIC)) {
+        // more images than resident CTAs: heavy-first order + dynamic scheduling
+        if (int e = launch_order(p.num_gt, p.B, p.M, p.order, st)) return e;
+        pp.dynamic = 1;
+    }
+    return check_cuda(cudaLaunchKernelEx(&cfg, kern, pp), "launch mbx_match_loss_reg_kernel");
 }
 
 }  // namespace

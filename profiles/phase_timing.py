@@ -14,8 +14,14 @@ from multibox_b200 import _build, _lib, synth  # noqa: E402
 
 out_dir = os.path.join(ROOT, "gpurun_out")
 os.makedirs(out_dir, exist_ok=True)
-so = os.path.join(out_dir, "libmbx_timing.so")
-_build.build(force=True, extra_flags=("-DMBX_PHASE_TIMING",), lib=so)
+# built next to the product library (a git-ignored .so travels to the GPU box; gpurun_out/ does not),
+# so `python profiles/phase_timing.py --build-only` here saves the compile time on the box
+so = os.path.join(ROOT, "multibox_b200", "libmbx_timing.so")
+_src = [os.path.join(_build.CSRC, f) for f in os.listdir(_build.CSRC) if f.endswith((".cu", ".cuh"))]
+if not os.path.isfile(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in _src):
+    _build.build(force=True, extra_flags=("-DMBX_PHASE_TIMING",), lib=so)
+if "--build-only" in sys.argv:
+    sys.exit(0)
 _build.LIB = so
 _build.needs_build = lambda: False
 lib = _lib.load()
@@ -38,7 +44,7 @@ def dev(a):
 
 if detect_mode:
     from multibox_b200 import detect
-    dn = ["load/decode/keys", "sort", "suppression matrix", "sweep (+wait)", "store"]
+    dn = ["load/decode/keys", "select + sort", "NMS: chunk triangles", "NMS: resolve + cross-chunk", "store"]
     for label, kw in (("cfg3", dict(K=5, B=148, keep=200, seed=1003)), ("K=11", dict(K=11, B=148, keep=200, seed=4))):
         q = synth.make_detect_inputs(**kw)
         B = q["B"]
@@ -74,3 +80,21 @@ for label, d in (("cfg2", synth.make_train_inputs(**synth.TRAIN_CONFIGS["cfg2"])
         for k, nm in enumerate(names):
             print("   %-16s %9.0f  (%.0f per augmentation)" % (nm, tot[k], tot[k] / max(1, d["num_gt"][b])))
         print("   total %.0f cycles; slowest warp %.0f" % (tot.sum(), t[b].sum(1).max()))
+
+# COCO-person-shaped images (K=7, P=904, M=100): the per-image fixed costs at small GT counts
+d = synth.make_train_inputs(K=7, B=148, M=100, dist="coco_person", seed=1004)
+B, P = d["B"], d["P"]
+for w in ([warps] if warps else [8]):
+    out = {"mask": torch.zeros(max(B * P, B * 16 * 8 * 2 * 4 + 64), dtype=torch.int32, device="cuda")}
+    for _ in range(2):
+        loss.match_loss_raw(dev(d["locations"]), dev(d["confidences"]).view(B, P), dev(d["gt"]), dev(d["num_gt"]),
+                            dev(d["priors"]), d["alpha"], want_mask=True, warps=w, out=out)
+    torch.cuda.synchronize()
+    t = out["mask"].cpu().numpy().view(np.int64)[:B * w * 8].reshape(B, w, 8)
+    for want in (0, 3, 8, int(d["num_gt"].max())):
+        sel = np.where(d["num_gt"] == want)[0]
+        if len(sel) == 0:
+            continue
+        tot = t[sel].mean(0).mean(0)
+        print("cfg4-shape warps=%d: %d images with n=%d, mean cycles by phase: %s  total %.0f" %
+              (w, len(sel), want, " ".join("%s=%.0f" % (nm.split()[0], tot[k]) for k, nm in enumerate(names)), tot.sum()))

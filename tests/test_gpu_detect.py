@@ -95,6 +95,32 @@ def test_detect_nms_heavy_overlap(cuda_device):
     _compare(_run(d, nms_iou=0.5), post)
 
 
+@pytest.mark.parametrize("thr", [0.5, 1.0 / 3.0, 0.25, 0.75, 0.0, 1e-8, 2.0])
+def test_detect_nms_threshold_ties(cuda_device, thr):
+    """Lattice-valued boxes (zero priors, so decode is the identity): many IoUs equal the
+    threshold EXACTLY or sit within an ulp of it, zero-area boxes give 0/0.  The kernel's
+    division-free decision must hand every such pair to the exact path (strict >, NaN false)."""
+    d = synth.make_detect_inputs(K=5, B=8, keep=200, seed=21)
+    rng = np.random.default_rng(22)
+    B, P = d["B"], d["P"]
+    for b in range(B):
+        lat = (4, 8, 16, 3)[b % 4]
+        p = rng.integers(0, lat + 1, size=(P, 4)).astype(np.float32) / np.float32(lat)
+        box = np.stack([np.minimum(p[:, 0], p[:, 2]), np.minimum(p[:, 1], p[:, 3]),
+                        np.maximum(p[:, 0], p[:, 2]), np.maximum(p[:, 1], p[:, 3])], 1)
+        if b in (3, 6):   # corners NOT ordered: x2 < x1 boxes, negative areas / denominators (no fix-up in the reference)
+            box = p
+        if b >= 4:   # a jittered copy: IoUs a few ulp either side of simple fractions
+            box = (box * np.float32(1.0 + 3e-7)).astype(np.float32)
+        d["locations"][b] = box
+    d["priors"] = np.zeros_like(d["priors"])
+    post = np_oracle.postprocess(d["locations"], d["confidences"], d["priors"], d["restrictions"],
+                                 d["max_to_keep"], d["offsets"], d["patch_dims"], d["image_dims"],
+                                 d["is_flipped"], nms_iou=thr)
+    for warps in (0, 4, 16):
+        _compare(_run(d, nms_iou=thr, warps=warps), post)
+
+
 def test_detect_logits(cuda_device):
     d = synth.make_detect_inputs(K=5, B=6, keep=100, seed=5)
     out = _run(d, logits=True)

@@ -151,3 +151,33 @@ def test_determinism(cuda_device):
     b = _run_gpu(d, 1000.0)
     assert np.array_equal(a["results"].view(np.uint32), b["results"].view(np.uint32))
     assert np.array_equal(a["d_confidences"].view(np.uint32), b["d_confidences"].view(np.uint32))
+
+
+def test_dynamic_schedule_matches_static(cuda_device):
+    """More images than resident CTAs: the heavy-first dynamically scheduled launch must give
+    bit-identical losses, gradients and matches to the static image -> CTA assignment
+    (per-image partials are reduced in image order whatever the processing order), run after
+    run (the scheduler's queue counter is re-armed by each launch)."""
+    from multibox_b200 import _lib
+    d = synth.make_train_inputs(K=7, B=1500, M=100, dist="coco_person", seed=4)
+
+    def run(flags):
+        out = loss.match_loss_raw(dev(d["locations"]), dev(d["confidences"]).view(d["B"], d["P"]), dev(d["gt"]),
+                                  dev(d["num_gt"]), dev(d["priors"]), 1000.0, flags=flags, want_mask=True,
+                                  want_gt_idx=True, want_stacked=True, want_grads=True)
+        torch.cuda.synchronize()
+        return {k: v.cpu().numpy() for k, v in out.items()}
+
+    st = run(_lib.FLAG_STATIC)
+    assert st["results"][2] == 0
+    for _ in range(3):
+        dy = run(0)
+        for k in ("mask", "matched_gt_idx", "stacked_gt", "d_locations", "d_confidences"):
+            assert np.array_equal(st[k], dy[k]), k
+        assert np.array_equal(st["results"][:8].view(np.uint32), dy["results"][:8].view(np.uint32))
+    # and both agree with the oracle on a sample of images
+    sub = slice(0, 64)
+    ref = np_oracle.add_loss(d["locations"][sub], d["confidences"][sub], d["gt"][sub], d["num_gt"][sub], d["priors"],
+                             1000.0)
+    P = d["P"]
+    assert np.array_equal(dy["matched_gt_idx"].reshape(-1)[:64 * P], ref["matched_gt_idx"])
