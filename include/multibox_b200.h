@@ -49,6 +49,7 @@ extern "C" {
 #define MBX_STATUS_AR_TIMEOUT    8u  /* fused loss all-reduce: a peer rank never arrived */
 
 #define MBX_MAX_PEERS 8              /* GPUs of one NVLink/NVSwitch box */
+#define MBX_MAX_HEADS 8              /* detection heads (the reference has 6: 8x8, 6x6, 4x4, 3x3, 2x2, 1x1) */
 
 /* flags */
 #define MBX_FLAG_LOGITS        1u   /* `confidences` holds logits; the kernel applies the
@@ -127,6 +128,50 @@ int mbx_match_loss(const float *locations, const float *confidences,
                    float *confidences_out, float *results,
                    void *workspace, size_t workspace_bytes, void *stream);
 
+/* Ragged ground truth (CSR) instead of the zero-padded [B,M,4] block the reference's input
+ * pipeline builds (inputs.py:340-348, eval_inputs.py:78-93): image b owns rows
+ * gt_row_offsets[b] .. gt_row_offsets[b+1]-1 of gt_flat [N,4]; gt_row_offsets is int32 [B+1],
+ * non-decreasing.  M is only the per-image capacity (an image with more than M rows trips
+ * MBX_STATUS_BAD_NUM_GT and is clamped).  Saves the 16*(M - n) padding bytes per image; every
+ * other argument and every result is as in mbx_match_loss. */
+int mbx_match_loss_ragged(const float *locations, const float *confidences,
+                          const float *gt_flat, const int32_t *gt_row_offsets,
+                          const float *priors, int B, int P, int M, float alpha,
+                          unsigned flags,
+                          int32_t *mask, int32_t *matched_gt_idx,
+                          float *stacked_gt, int32_t *n_stacked,
+                          float *d_locations, float *d_confidences,
+                          float *confidences_out, float *results,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* Head-layout inputs: the training hot path fed straight from the detection heads' conv
+ * outputs, replacing the reshape + tf.concat (+ tf.sigmoid with MBX_FLAG_LOGITS) of reference
+ * model.py:295-322.  Head h (grid g_h x g_h, K_h boxes per cell; the reference has the six grids
+ * 8,6,4,3,2,1 in this order) contributes head_priors[h] = g_h*g_h*K_h consecutive priors; its
+ * NHWC conv outputs [B,g,g,K*4] / [B,g,g,K] are exactly [B,head_priors[h],4] / [B,head_priors[h]].
+ * Gradients come back in the same per-head layouts (all heads or none), so neither the
+ * concatenated [B,P,4] / [B,P] tensors nor their gradients ever exist in HBM.  mask /
+ * matched_gt_idx / confidences_out stay in the concatenated prior order [B,P]. */
+typedef struct mbx_heads {
+    int32_t num_heads;                          /* 1 .. MBX_MAX_HEADS */
+    int32_t head_priors[MBX_MAX_HEADS];         /* sum == P */
+    const float *locations[MBX_MAX_HEADS];      /* [B, head_priors[h], 4] */
+    const float *confidences[MBX_MAX_HEADS];    /* [B, head_priors[h]] (logits with MBX_FLAG_LOGITS) */
+    float *d_locations[MBX_MAX_HEADS];          /* NULL = gradient not wanted */
+    float *d_confidences[MBX_MAX_HEADS];
+} mbx_heads;
+
+/* gt: padded (gt_row_offsets == NULL, num_gt given) or ragged (gt_row_offsets given, num_gt ignored).
+ * MBX_FLAG_BOUNDARY is not available (the heads produce offsets, not absolute boxes). */
+int mbx_match_loss_heads(const mbx_heads *heads,
+                         const float *gt_bboxes, const int32_t *num_gt, const int32_t *gt_row_offsets,
+                         const float *priors, int B, int P, int M, float alpha,
+                         unsigned flags,
+                         int32_t *mask, int32_t *matched_gt_idx,
+                         float *stacked_gt, int32_t *n_stacked,
+                         float *confidences_out, float *results,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
 /* Same as mbx_match_loss, with the SUM all-reduce of the two loss scalars over the
  * `world` GPUs of one NVLink box FUSED into the kernel (reference semantics: the losses
  * are batch sums, loss.py:100-101; the batch is sharded by image, one process per GPU).
@@ -172,9 +217,12 @@ size_t mbx_detect_workspace_bytes(int B, int P, int k_max);
  * greedy NMS on the kept boxes (extension: no reference counterpart), and
  * convert_proposals (:106-131, float64).  With restrictions [0,0,1,1] and
  * nms_iou < 0 it is also the decode/sort/top-k of reference eval.py:146-167.
+ * A confidence of -inf marks an empty slot: such a prior is never a proposal (used by pooled
+ * multi-patch candidate lists; no sigmoid output is -inf, so reference inputs are unaffected).
  *
  * Inputs
  *   locations    [B,P,4], confidences [B,P] (logits with MBX_FLAG_LOGITS), priors [P,4]
+ *                (priors NULL = the locations are absolute boxes already; nothing is staged)
  *   restrictions [B,4]   float32 x1,y1,x2,y2 limits (NULL = [0,0,1,1] everywhere)
  *   max_to_keep  [B]     int32 (NULL = k_max everywhere); clamped to k_max
  *   offsets      [B,2]   int32 (y,x) patch offset    } NULL = identity conversion
@@ -197,6 +245,18 @@ int mbx_detect(const float *locations, const float *confidences, const float *pr
                double *out_boxes, float *out_patch_boxes, float *out_scores,
                int32_t *out_prior_idx, int32_t *out_count,
                void *workspace, size_t workspace_bytes, void *stream);
+
+/* mbx_detect fed straight from the detection heads' conv outputs (see mbx_heads above): decode,
+ * sigmoid (MBX_FLAG_LOGITS), filter, top-k, NMS and conversion without the reshape + concat of
+ * reference model.py:295-322.  Only heads->locations / confidences / head_priors are read. */
+int mbx_detect_heads(const mbx_heads *heads, const float *priors,
+                     const float *restrictions, const int32_t *max_to_keep,
+                     const int32_t *offsets, const int32_t *patch_dims,
+                     const int32_t *image_dims, const int32_t *is_flipped,
+                     int B, int P, int k_max, float nms_iou, unsigned flags,
+                     double *out_boxes, float *out_patch_boxes, float *out_scores,
+                     int32_t *out_prior_idx, int32_t *out_count,
+                     void *workspace, size_t workspace_bytes, void *stream);
 
 /* Batched filter_proposals (reference detect.py:74-104): order-preserving
  * compaction of the boxes that lie inside the restriction rectangle.

@@ -32,13 +32,24 @@ MAX_PEERS = 8
 RESULT_WORDS = 16
 
 EXPORTS = ("mbx_version", "mbx_last_error", "mbx_device_info",
-           "mbx_match_workspace_bytes", "mbx_match_loss",
+           "mbx_match_workspace_bytes", "mbx_match_loss", "mbx_match_loss_ragged", "mbx_match_loss_heads",
            "mbx_allreduce_buffer_bytes", "mbx_match_loss_allreduce", "mbx_allreduce_flush",
-           "mbx_detect_workspace_bytes", "mbx_detect",
+           "mbx_detect_workspace_bytes", "mbx_detect", "mbx_detect_heads",
            "mbx_filter_proposals", "mbx_convert_proposals",
            "mbx_debug_nplog", "mbx_debug_cost_matrix", "mbx_debug_sqrt_mismatches")
 
 _lib = None
+MAX_HEADS = 8
+
+
+class Heads(ctypes.Structure):
+    """ctypes image of `mbx_heads` (include/multibox_b200.h)."""
+    _fields_ = [("num_heads", ctypes.c_int32),
+                ("head_priors", ctypes.c_int32 * MAX_HEADS),
+                ("locations", ctypes.c_void_p * MAX_HEADS),
+                ("confidences", ctypes.c_void_p * MAX_HEADS),
+                ("d_locations", ctypes.c_void_p * MAX_HEADS),
+                ("d_confidences", ctypes.c_void_p * MAX_HEADS)]
 
 
 class MultiboxLibraryError(RuntimeError):
@@ -76,6 +87,15 @@ def load():
         _c_void_p, _c_void_p, _c_void_p, _c_void_p,                 # mask, matched_gt_idx, stacked_gt, n_stacked
         _c_void_p, _c_void_p, _c_void_p, _c_void_p,                 # d_loc, d_conf, conf_out, results
         _c_void_p, _c_size_t, _c_void_p]                            # workspace, bytes, stream
+    lib.mbx_match_loss_ragged.restype = _c_int
+    lib.mbx_match_loss_ragged.argtypes = lib.mbx_match_loss.argtypes    # gt_flat, gt_row_offsets in place of gt, num_gt
+    lib.mbx_match_loss_heads.restype = _c_int
+    lib.mbx_match_loss_heads.argtypes = [
+        ctypes.POINTER(Heads), _c_void_p, _c_void_p, _c_void_p, _c_void_p,   # heads, gt, num_gt, gt_row_offsets, priors
+        _c_int, _c_int, _c_int, _c_float, _c_uint,                  # B, P, M, alpha, flags
+        _c_void_p, _c_void_p, _c_void_p, _c_void_p,                 # mask, matched_gt_idx, stacked_gt, n_stacked
+        _c_void_p, _c_void_p,                                       # conf_out, results
+        _c_void_p, _c_size_t, _c_void_p]                            # workspace, bytes, stream
     lib.mbx_allreduce_buffer_bytes.restype = _c_size_t
     lib.mbx_allreduce_buffer_bytes.argtypes = []
     lib.mbx_match_loss_allreduce.restype = _c_int
@@ -91,6 +111,8 @@ def load():
         _c_int, _c_int, _c_int, _c_float, _c_uint,                  # B, P, k_max, nms_iou, flags
         _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,      # out_boxes, out_patch_boxes, out_scores, out_idx, out_count
         _c_void_p, _c_size_t, _c_void_p]                            # workspace, bytes, stream
+    lib.mbx_detect_heads.restype = _c_int
+    lib.mbx_detect_heads.argtypes = [ctypes.POINTER(Heads)] + lib.mbx_detect.argtypes[2:]
     lib.mbx_filter_proposals.restype = _c_int
     lib.mbx_filter_proposals.argtypes = [
         _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,            # bboxes, confidences, restrictions, B, P

@@ -122,6 +122,32 @@ __device__ __forceinline__ float nplogf(float x_in) {
 // sigmoid of reference model.py:322 (fp32; tolerance-checked, not bit-pinned)
 __device__ __forceinline__ float sigmoidf_(float z) { return __fdiv_rn(1.0f, 1.0f + expf(-z)); }
 
+// ---------------------------------------------------------------- per-head input layout
+// One detection head of the reference network (model.py:198-316): its conv outputs, NHWC, are
+// [B, g, g, K*4] / [B, g, g, K] = [B, pri, 4] / [B, pri] with pri = g*g*K consecutive priors.
+struct HeadTab {
+    const float *loc, *conf;
+    float *dloc, *dconf;
+    int pri, off;   // priors of this head; index of its first prior in the concatenated order
+};
+
+// The head table staged in shared memory (dynamic indexing of kernel parameters would force a
+// local-memory copy of the whole parameter block).  Call with all threads, then barrier.
+template <typename Params>
+__device__ __forceinline__ void stage_heads(const Params &p, HeadTab *sh) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < MBX_MAX_HEADS; ++k) sh[k] = p.heads[k];
+    }
+}
+// element index of prior j of image b inside its head's tensors; h = the head
+__device__ __forceinline__ size_t head_elem(const HeadTab *sh, int nheads, int j, int b, int &h) {
+    h = 0;
+    for (int k = 1; k < nheads; ++k) h += (j >= sh[k].off) ? 1 : 0;
+    return static_cast<size_t>(b) * sh[h].pri + (j - sh[h].off);
+}
+
+
 // ---------------------------------------------------------------- warp / block reductions
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

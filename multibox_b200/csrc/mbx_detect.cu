@@ -39,6 +39,8 @@ struct DetectParams {
     const float *locations, *confidences, *priors, *restrictions;
     const int32_t *max_to_keep, *offsets, *patch_dims, *image_dims, *is_flipped;
     int B, P, k_max, n2;
+    int nheads;                       // > 1: inputs come per head (model.py:295-320 never materialised)
+    HeadTab heads[MBX_MAX_HEADS];
     float nms_iou;
     unsigned flags;
     double *out_boxes;
@@ -108,7 +110,8 @@ struct DSmem {
 
 __host__ __device__ inline size_t dalign(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline size_t dcarve(DSmem *s, unsigned char *base, int P, int n2, int k_max, bool nms) {
+__host__ __device__ inline size_t dcarve(DSmem *s, unsigned char *base, int P, int n2, int k_max, bool nms,
+                                         bool has_priors) {
     const int W = (k_max + 31) / 32;
     size_t o = 0;
     auto take = [&](size_t bytes, size_t al) {
@@ -117,7 +120,7 @@ __host__ __device__ inline size_t dcarve(DSmem *s, unsigned char *base, int P, i
         o += bytes;
         return r;
     };
-    size_t o_pri = take(sizeof(float4) * P, 16);
+    size_t o_pri = take(has_priors ? sizeof(float4) * P : 0, 16);
     size_t o_box = take(sizeof(float4) * P, 16);
     size_t o_sbox = take(nms ? sizeof(float4) * (W * 32) : 0, 16);   // padded to whole 32-row blocks
     size_t o_keys = take(sizeof(unsigned long long) * n2, 8);
@@ -233,21 +236,25 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DSmem s;
     const bool nms = p.nms_iou >= 0.0f;
-    dcarve(&s, smem_raw, p.P, p.n2, p.k_max, nms);
+    const bool has_priors = p.priors != nullptr;   // NULL: the locations are absolute boxes already
+    dcarve(&s, smem_raw, p.P, p.n2, p.k_max, nms, has_priors);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = p.P, N2 = p.n2, KM = p.k_max;
     const bool logits = (p.flags & MBX_FLAG_LOGITS) != 0;
 
+    __shared__ HeadTab sh_heads[MBX_MAX_HEADS];
+    const int nheads = p.nheads;
+    if (nheads > 1) stage_heads(p, sh_heads);
     if (tid == 0) {
         mbar_init(s.bar, 1);
         fence_mbar_init();
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && has_priors) {
         mbar_arrive_expect_tx(s.bar, static_cast<uint32_t>(sizeof(float4) * P));
         bulk_copy_g2s(s.priors, p.priors, static_cast<uint32_t>(sizeof(float4) * P), s.bar);
     }
-    bool priors_ready = false;
+    bool priors_ready = !has_priors;
 #ifdef MBX_PHASE_TIMING
     long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long t_last = clock64();
@@ -273,17 +280,28 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
         for (int j = tid; j < N2; j += T) {
             unsigned long long key = 0ull;
             if (j < P) {
-                float4 l = ld_stream_f4(gl + j);
-                const float4 q = s.priors[j];
+                float4 l;
+                float c;
+                if (nheads > 1) {
+                    int hh;
+                    const size_t e = head_elem(sh_heads, nheads, j, b, hh);
+                    l = ld_stream_f4(reinterpret_cast<const float4 *>(sh_heads[hh].loc) + e);
+                    c = ld_stream_f(sh_heads[hh].conf + e);
+                } else {
+                    l = ld_stream_f4(gl + j);
+                    c = ld_stream_f(p.confidences + row0 + j);
+                }
+                const float4 q = has_priors ? s.priors[j] : make_float4(0.f, 0.f, 0.f, 0.f);
                 l.x = clip01(__fadd_rn(l.x, q.x));
                 l.y = clip01(__fadd_rn(l.y, q.y));
                 l.z = clip01(__fadd_rn(l.z, q.z));
                 l.w = clip01(__fadd_rn(l.w, q.w));
                 s.box[j] = l;
-                float c = ld_stream_f(p.confidences + row0 + j);
                 if (logits) c = sigmoidf_(c);
                 c = __fadd_rn(c, 0.0f);   // -0.0 -> +0.0 so equal values share one key
-                const bool drop = (l.x < r.x) || (l.y < r.y) || (l.z > r.z) || (l.w > r.w);   // detect.py:92-99
+                // detect.py:92-99; a confidence of -inf marks a slot that holds no proposal (padding of
+                // pooled candidate lists, multibox_b200/patches.py) -- no sigmoid output is ever -inf
+                const bool drop = (l.x < r.x) || (l.y < r.y) || (l.z > r.z) || (l.w > r.w) || (c == -CUDART_INF_F);
                 if (!drop) {
                     key = (static_cast<unsigned long long>(orderable(c)) << 32) | static_cast<unsigned>(j);
                     atomicAdd(&s.hist[conf_bin(c)], 1);
@@ -801,23 +819,35 @@ extern "C" size_t mbx_detect_workspace_bytes(int B, int P, int k_max) {
     return 256;   // the detect path needs no global scratch; kept in the ABI for symmetry
 }
 
-extern "C" int mbx_detect(const float *locations, const float *confidences, const float *priors,
-                          const float *restrictions, const int32_t *max_to_keep, const int32_t *offsets,
-                          const int32_t *patch_dims, const int32_t *image_dims, const int32_t *is_flipped, int B,
-                          int P, int k_max, float nms_iou, unsigned flags, double *out_boxes,
-                          float *out_patch_boxes, float *out_scores, int32_t *out_prior_idx, int32_t *out_count,
-                          void *workspace, size_t workspace_bytes, void *stream) {
-    (void)workspace;
-    (void)workspace_bytes;
+namespace mbx {
+static int detect_impl(const mbx_heads *heads, const float *locations, const float *confidences, const float *priors,
+                       const float *restrictions, const int32_t *max_to_keep, const int32_t *offsets,
+                       const int32_t *patch_dims, const int32_t *image_dims, const int32_t *is_flipped, int B, int P,
+                       int k_max, float nms_iou, unsigned flags, double *out_boxes, float *out_patch_boxes,
+                       float *out_scores, int32_t *out_prior_idx, int32_t *out_count, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (B < 0 || P <= 0 || k_max <= 0) {
         set_error("mbx_detect: bad sizes B=%d P=%d k_max=%d", B, P, k_max);
         return MBX_E_ARG;
     }
     if (B == 0) return 0;
-    if (!locations || !confidences || !priors) {
+    if (!heads && (!locations || !confidences)) {
         set_error("mbx_detect: null input pointer");
         return MBX_E_ARG;
+    }
+    if (heads) {
+        int tot = 0;
+        bool bad = heads->num_heads < 1 || heads->num_heads > MBX_MAX_HEADS;
+        for (int k = 0; !bad && k < heads->num_heads; ++k) {
+            bad = heads->head_priors[k] <= 0 || !heads->locations[k] || !heads->confidences[k] ||
+                  (reinterpret_cast<uintptr_t>(heads->locations[k]) & 15u);
+            tot += heads->head_priors[k];
+        }
+        if (bad || tot != P) {
+            set_error("mbx_detect_heads: bad head table (num_heads=%d, sum of head_priors=%d, P=%d)",
+                      heads->num_heads, tot, P);
+            return MBX_E_ARG;
+        }
     }
     if ((image_dims != nullptr) != (patch_dims != nullptr) || (image_dims != nullptr) != (offsets != nullptr)) {
         set_error("mbx_detect: offsets, patch_dims and image_dims must be given together");
@@ -835,6 +865,20 @@ extern "C" int mbx_detect(const float *locations, const float *confidences, cons
     DetectParams p;
     p.locations = locations;
     p.confidences = confidences;
+    p.nheads = 1;
+    for (int k = 0; k < MBX_MAX_HEADS; ++k) p.heads[k] = HeadTab{nullptr, nullptr, nullptr, nullptr, 0, 0};
+    if (heads) {
+        int off = 0;
+        p.nheads = heads->num_heads;
+        for (int k = 0; k < heads->num_heads; ++k) {
+            p.heads[k] = HeadTab{heads->locations[k], heads->confidences[k], nullptr, nullptr, heads->head_priors[k], off};
+            off += heads->head_priors[k];
+        }
+        if (p.nheads == 1) {
+            p.locations = heads->locations[0];
+            p.confidences = heads->confidences[0];
+        }
+    }
     p.priors = priors;
     p.restrictions = restrictions;
     p.max_to_keep = max_to_keep;
@@ -857,7 +901,7 @@ extern "C" int mbx_detect(const float *locations, const float *confidences, cons
     p.out_scores = out_scores;
     p.out_idx = out_prior_idx;
     p.out_count = out_count;
-    const size_t smem = dcarve(nullptr, nullptr, P, n2, k_max, nms_iou >= 0.0f);
+    const size_t smem = dcarve(nullptr, nullptr, P, n2, k_max, nms_iou >= 0.0f, priors != nullptr);
     if (smem > static_cast<size_t>(max_smem_optin())) {
         set_error("mbx_detect: P=%d k_max=%d needs %zu bytes of shared memory per CTA (max %d)", P, k_max, smem,
                   max_smem_optin());
@@ -871,4 +915,35 @@ extern "C" int mbx_detect(const float *locations, const float *confidences, cons
             set_error("mbx_detect: forced warps must be 4, 8 or 16");
             return MBX_E_ARG;
     }
+}
+}  // namespace mbx
+
+extern "C" int mbx_detect(const float *locations, const float *confidences, const float *priors,
+                          const float *restrictions, const int32_t *max_to_keep, const int32_t *offsets,
+                          const int32_t *patch_dims, const int32_t *image_dims, const int32_t *is_flipped, int B,
+                          int P, int k_max, float nms_iou, unsigned flags, double *out_boxes,
+                          float *out_patch_boxes, float *out_scores, int32_t *out_prior_idx, int32_t *out_count,
+                          void *workspace, size_t workspace_bytes, void *stream) {
+    (void)workspace;
+    (void)workspace_bytes;
+    return detect_impl(nullptr, locations, confidences, priors, restrictions, max_to_keep, offsets, patch_dims,
+                       image_dims, is_flipped, B, P, k_max, nms_iou, flags, out_boxes, out_patch_boxes, out_scores,
+                       out_prior_idx, out_count, stream);
+}
+
+extern "C" int mbx_detect_heads(const mbx_heads *heads, const float *priors, const float *restrictions,
+                                const int32_t *max_to_keep, const int32_t *offsets, const int32_t *patch_dims,
+                                const int32_t *image_dims, const int32_t *is_flipped, int B, int P, int k_max,
+                                float nms_iou, unsigned flags, double *out_boxes, float *out_patch_boxes,
+                                float *out_scores, int32_t *out_prior_idx, int32_t *out_count, void *workspace,
+                                size_t workspace_bytes, void *stream) {
+    (void)workspace;
+    (void)workspace_bytes;
+    if (!heads) {
+        set_error("mbx_detect_heads: null heads");
+        return MBX_E_ARG;
+    }
+    return detect_impl(heads, nullptr, nullptr, priors, restrictions, max_to_keep, offsets, patch_dims, image_dims,
+                       is_flipped, B, P, k_max, nms_iou, flags, out_boxes, out_patch_boxes, out_scores, out_prior_idx,
+                       out_count, stream);
 }

@@ -135,14 +135,15 @@ __host__ __device__ inline size_t carve(Smem *s, unsigned char *base, int P, int
 // per-image partials are reduced in image order).  An image's solve time grows with its GT count,
 // so handing out the heavy images first bounds the tail of the launch by a LIGHT image's time
 // (longest-processing-time-first list scheduling).  One CTA of 1024 threads.
-__global__ void __launch_bounds__(1024) mbx_order_kernel(const int32_t *num_gt, int B, int M, int32_t *order) {
+__global__ void __launch_bounds__(1024) mbx_order_kernel(const int32_t *num_gt, const int32_t *gt_row, int B, int M,
+                                                         int32_t *order) {
     __shared__ int hist[256], start[256];
     const int tid = threadIdx.x;
     const int shift = M < 256 ? 0 : (32 - __clz(M >> 8));   // bucket = n >> shift < 256
     if (tid < 256) hist[tid] = 0;
     __syncthreads();
     for (int b = tid; b < B; b += 1024) {
-        int n = num_gt[b];
+        int n = image_num_gt(num_gt, gt_row, b);
         n = n < 0 ? 0 : (n > M ? M : n);
         atomicAdd(&hist[n >> shift], 1);
     }
@@ -166,20 +167,20 @@ __global__ void __launch_bounds__(1024) mbx_order_kernel(const int32_t *num_gt, 
     }
     __syncthreads();
     for (int b = tid; b < B; b += 1024) {
-        int n = num_gt[b];
+        int n = image_num_gt(num_gt, gt_row, b);
         n = n < 0 ? 0 : (n > M ? M : n);
         order[atomicAdd(&start[n >> shift], 1)] = b;
     }
 }
 
-int launch_order(const int32_t *num_gt, int B, int M, int32_t *order, cudaStream_t st) {
-    mbx_order_kernel<<<1, 1024, 0, st>>>(num_gt, B, M, order);
+int launch_order(const int32_t *num_gt, const int32_t *gt_row, int B, int M, int32_t *order, cudaStream_t st) {
+    mbx_order_kernel<<<1, 1024, 0, st>>>(num_gt, gt_row, B, M, order);
     return check_cuda(cudaGetLastError(), "launch mbx_order_kernel");
 }
 
 // exclusive scan of clamp(num_gt, 0, M) -> offsets[B+1]; one CTA of 1024 threads.
-__global__ void __launch_bounds__(1024) mbx_scan_num_gt_kernel(const int32_t *num_gt, int B, int M,
-                                                               int32_t *offsets, int32_t *n_stacked) {
+__global__ void __launch_bounds__(1024) mbx_scan_num_gt_kernel(const int32_t *num_gt, const int32_t *gt_row, int B,
+                                                               int M, int32_t *offsets, int32_t *n_stacked) {
     __shared__ int warp_excl[32];
     __shared__ int carry;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(1024) mbx_scan_num_gt_kernel(const int32_t *nu
         const int i = base + tid;
         int x = 0;
         if (i < B) {
-            x = num_gt[i];
+            x = image_num_gt(num_gt, gt_row, i);
             x = x < 0 ? 0 : (x > M ? M : x);
         }
         int inc = x;   // inclusive scan inside the warp
@@ -254,7 +255,8 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_kernel(const Match
     int pbuf = 0;
 
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-        int n = p.num_gt[b];
+        const float4 *gg;
+        int n = image_gt(p, b, gg);
         if (n < 0 || n > M) {
             status |= MBX_STATUS_BAD_NUM_GT;
             n = n < 0 ? 0 : M;
@@ -292,7 +294,6 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_kernel(const Match
             s.row4col[j] = -1;
             s.sc[j] = 0;
         }
-        const float4 *gg = reinterpret_cast<const float4 *>(p.gt) + static_cast<size_t>(b) * M;
         for (int i = tid; i < n; i += T) {
             s.gt[i] = gg[i];
             s.u[i] = 0.0;
@@ -664,15 +665,54 @@ extern "C" size_t mbx_match_workspace_bytes(int B, int P, int M) {
     return ws_layout(B < 1 ? 1 : B).total;
 }
 
+namespace mbx {
+int match_loss_impl(const mbx_heads *heads, const float *locations, const float *confidences,
+                           const float *gt_bboxes, const int32_t *num_gt, const int32_t *gt_row,
+                           const float *priors, int B, int P, int M, float alpha, unsigned flags, int32_t *mask,
+                           int32_t *matched_gt_idx, float *stacked_gt, int32_t *n_stacked, float *d_locations,
+                           float *d_confidences, float *confidences_out, float *results, void *workspace,
+                           size_t workspace_bytes, const unsigned long long *peer_buffers, int world, int rank,
+                           void *stream);
+}
+
 extern "C" int mbx_match_loss(const float *locations, const float *confidences, const float *gt_bboxes,
                               const int32_t *num_gt, const float *priors, int B, int P, int M, float alpha,
                               unsigned flags, int32_t *mask, int32_t *matched_gt_idx, float *stacked_gt,
                               int32_t *n_stacked, float *d_locations, float *d_confidences,
                               float *confidences_out, float *results, void *workspace, size_t workspace_bytes,
                               void *stream) {
-    return mbx_match_loss_allreduce(locations, confidences, gt_bboxes, num_gt, priors, B, P, M, alpha, flags, mask,
-                                    matched_gt_idx, stacked_gt, n_stacked, d_locations, d_confidences,
-                                    confidences_out, results, workspace, workspace_bytes, nullptr, 1, 0, stream);
+    return match_loss_impl(nullptr, locations, confidences, gt_bboxes, num_gt, nullptr, priors, B, P, M, alpha, flags,
+                           mask, matched_gt_idx, stacked_gt, n_stacked, d_locations, d_confidences, confidences_out,
+                           results, workspace, workspace_bytes, nullptr, 1, 0, stream);
+}
+
+extern "C" int mbx_match_loss_ragged(const float *locations, const float *confidences, const float *gt_flat,
+                                     const int32_t *gt_row_offsets, const float *priors, int B, int P, int M,
+                                     float alpha, unsigned flags, int32_t *mask, int32_t *matched_gt_idx,
+                                     float *stacked_gt, int32_t *n_stacked, float *d_locations,
+                                     float *d_confidences, float *confidences_out, float *results,
+                                     void *workspace, size_t workspace_bytes, void *stream) {
+    if (!gt_row_offsets) {
+        set_error("mbx_match_loss_ragged: null gt_row_offsets");
+        return MBX_E_ARG;
+    }
+    return match_loss_impl(nullptr, locations, confidences, gt_flat, nullptr, gt_row_offsets, priors, B, P, M, alpha,
+                           flags, mask, matched_gt_idx, stacked_gt, n_stacked, d_locations, d_confidences,
+                           confidences_out, results, workspace, workspace_bytes, nullptr, 1, 0, stream);
+}
+
+extern "C" int mbx_match_loss_heads(const mbx_heads *heads, const float *gt_bboxes, const int32_t *num_gt,
+                                    const int32_t *gt_row_offsets, const float *priors, int B, int P, int M,
+                                    float alpha, unsigned flags, int32_t *mask, int32_t *matched_gt_idx,
+                                    float *stacked_gt, int32_t *n_stacked, float *confidences_out, float *results,
+                                    void *workspace, size_t workspace_bytes, void *stream) {
+    if (!heads) {
+        set_error("mbx_match_loss_heads: null heads");
+        return MBX_E_ARG;
+    }
+    return match_loss_impl(heads, nullptr, nullptr, gt_bboxes, num_gt, gt_row_offsets, priors, B, P, M, alpha, flags,
+                           mask, matched_gt_idx, stacked_gt, n_stacked, nullptr, nullptr, confidences_out, results,
+                           workspace, workspace_bytes, nullptr, 1, 0, stream);
 }
 
 extern "C" size_t mbx_allreduce_buffer_bytes(void) { return align_up(kArBytes, 256); }
@@ -723,6 +763,18 @@ extern "C" int mbx_match_loss_allreduce(const float *locations, const float *con
                                         void *workspace, size_t workspace_bytes,
                                         const unsigned long long *peer_buffers, int world, int rank,
                                         void *stream) {
+    return match_loss_impl(nullptr, locations, confidences, gt_bboxes, num_gt, nullptr, priors, B, P, M, alpha, flags,
+                           mask, matched_gt_idx, stacked_gt, n_stacked, d_locations, d_confidences, confidences_out,
+                           results, workspace, workspace_bytes, peer_buffers, world, rank, stream);
+}
+
+int mbx::match_loss_impl(const mbx_heads *heads, const float *locations, const float *confidences,
+                                const float *gt_bboxes, const int32_t *num_gt, const int32_t *gt_row,
+                                const float *priors, int B, int P, int M, float alpha, unsigned flags,
+                                int32_t *mask, int32_t *matched_gt_idx, float *stacked_gt, int32_t *n_stacked,
+                                float *d_locations, float *d_confidences, float *confidences_out, float *results,
+                                void *workspace, size_t workspace_bytes, const unsigned long long *peer_buffers,
+                                int world, int rank, void *stream) {
     if (world < 1 || world > MBX_MAX_PEERS || rank < 0 || rank >= world || (world > 1 && !peer_buffers)) {
         set_error("mbx_match_loss_allreduce: bad world=%d rank=%d (max %d ranks)", world, rank, MBX_MAX_PEERS);
         return MBX_E_ARG;
@@ -738,10 +790,32 @@ extern "C" int mbx_match_loss_allreduce(const float *locations, const float *con
         set_error("mbx_match_loss: MBX_FLAG_BOUNDARY and MBX_FLAG_LOGITS are exclusive");
         return MBX_E_ARG;
     }
-    if (!locations || !confidences || !num_gt || (M > 0 && !gt_bboxes) || (!boundary && !priors) || !workspace ||
-        !results) {
+    if ((!heads && (!locations || !confidences)) || (!num_gt && !gt_row) || (M > 0 && !gt_bboxes && !gt_row) ||
+        (!boundary && !priors) || !workspace || !results) {
         set_error("mbx_match_loss: null input / results / workspace pointer");
         return MBX_E_ARG;
+    }
+    if (heads) {
+        int tot = 0;
+        bool bad = heads->num_heads < 1 || heads->num_heads > MBX_MAX_HEADS || boundary;
+        for (int k = 0; !bad && k < heads->num_heads; ++k) {
+            bad = heads->head_priors[k] <= 0 || !heads->locations[k] || !heads->confidences[k] ||
+                  (reinterpret_cast<uintptr_t>(heads->locations[k]) & 15u) ||
+                  (reinterpret_cast<uintptr_t>(heads->d_locations[k]) & 15u) ||
+                  ((heads->d_locations[k] != nullptr) != (heads->d_locations[0] != nullptr)) ||
+                  ((heads->d_confidences[k] != nullptr) != (heads->d_confidences[0] != nullptr));
+            tot += heads->head_priors[k];
+        }
+        if (bad || tot != P) {
+            set_error("mbx_match_loss_heads: bad head table (num_heads=%d, sum of head_priors=%d, P=%d; no "
+                      "MBX_FLAG_BOUNDARY; pointers 16-byte aligned; gradients for all heads or none)",
+                      heads->num_heads, tot, P);
+            return MBX_E_ARG;
+        }
+        if (flags & MBX_FLAG_GENERIC) {
+            set_error("mbx_match_loss_heads: the per-head layout needs the register-resident kernel family");
+            return MBX_E_ARG;
+        }
     }
     auto mis16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) != 0; };
     if (mis16(locations) || mis16(gt_bboxes) || mis16(priors) || mis16(stacked_gt) || mis16(d_locations) ||
@@ -765,6 +839,24 @@ extern "C" int mbx_match_loss_allreduce(const float *locations, const float *con
     p.gt = gt_bboxes;
     p.priors = priors;
     p.num_gt = num_gt;
+    p.gt_row = gt_row;
+    p.nheads = 1;
+    for (int k = 0; k < MBX_MAX_HEADS; ++k) p.heads[k] = HeadTab{nullptr, nullptr, nullptr, nullptr, 0, 0};
+    if (heads) {
+        int off = 0;
+        p.nheads = heads->num_heads;
+        for (int k = 0; k < heads->num_heads; ++k) {
+            p.heads[k] = HeadTab{heads->locations[k], heads->confidences[k], heads->d_locations[k],
+                                 heads->d_confidences[k], heads->head_priors[k], off};
+            off += heads->head_priors[k];
+        }
+        if (p.nheads == 1) {   // a single head is the dense layout
+            p.locations = heads->locations[0];
+            p.confidences = heads->confidences[0];
+            d_locations = heads->d_locations[0];
+            d_confidences = heads->d_confidences[0];
+        }
+    }
     p.B = B;
     p.P = P;
     p.M = M;
@@ -797,7 +889,7 @@ extern "C" int mbx_match_loss_allreduce(const float *locations, const float *con
     int nwarps = static_cast<int>((flags >> MBX_FLAG_WARPS_SHIFT) & 0xffu);
     const int ncols = static_cast<int>((flags >> MBX_FLAG_COLS_SHIFT) & 0xffu);
     if (stacked_gt || n_stacked) {
-        mbx_scan_num_gt_kernel<<<1, 1024, 0, st>>>(num_gt, B, M, p.stk_offsets, n_stacked);
+        mbx_scan_num_gt_kernel<<<1, 1024, 0, st>>>(num_gt, gt_row, B, M, p.stk_offsets, n_stacked);
         if (int e = check_cuda(cudaGetLastError(), "launch mbx_scan_num_gt_kernel")) return e;
     }
     if (!(flags & MBX_FLAG_GENERIC)) {
@@ -805,6 +897,10 @@ extern "C" int mbx_match_loss_allreduce(const float *locations, const float *con
         const int ncl = static_cast<int>((flags >> MBX_FLAG_CLUSTER_SHIFT) & 0xfu);
         const int rc = launch_match_reg(p, nwarps, ncols, ncl, st);
         if (rc != MBX_E_TOO_LARGE) return rc;
+        if (p.nheads > 1) {
+            set_error("mbx_match_loss_heads: P=%d is beyond the register-resident kernel family", P);
+            return rc;
+        }
         if (nwarps > 8) nwarps = 8;
     }
     if (nwarps == 0) nwarps = P <= 256 ? 2 : (P <= 1024 ? 4 : 8);

@@ -274,6 +274,9 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     const double INF = CUDART_INF;
     unsigned status = 0;
 
+    __shared__ HeadTab sh_heads[MBX_MAX_HEADS];
+    const int nheads = p.nheads;
+    if (nheads > 1) stage_heads(p, sh_heads);
     if (has_priors) {
         if (tid == 0) {
             mbar_init(s.bar, 1);
@@ -284,6 +287,8 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             mbar_arrive_expect_tx(s.bar, static_cast<uint32_t>(sizeof(float4) * P));
             bulk_copy_g2s(s.priors, p.priors, static_cast<uint32_t>(sizeof(float4) * P), s.bar);
         }
+    } else if (nheads > 1) {
+        block_sync<NWARPS>();
     }
     bool priors_ready = !has_priors;
     int pbuf = 0;
@@ -314,7 +319,8 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
         const int b = dyn ? p.order[q] : q;
         unsigned claim = 0u;
         if (dyn && tid == 0) claim = atomicAdd(p.queue, 1u);
-        int n = p.num_gt[b];
+        const float4 *gg;
+        int n = image_gt(p, b, gg);
         if (n < 0 || n > M) {
             status |= MBX_STATUS_BAD_NUM_GT;
             n = n < 0 ? 0 : M;
@@ -338,8 +344,15 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             loc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
             cf[c] = 0.5f;
             if (j < P) {
-                loc[c] = ld_stream_f4(gl + j);
-                cf[c] = ld_stream_f(p.confidences + row0 + j);
+                if (nheads > 1) {   // straight from the per-head conv outputs (model.py:295-320 never materialised)
+                    int hh;
+                    const size_t e = head_elem(sh_heads, nheads, j, b, hh);
+                    loc[c] = ld_stream_f4(reinterpret_cast<const float4 *>(sh_heads[hh].loc) + e);
+                    cf[c] = ld_stream_f(sh_heads[hh].conf + e);
+                } else {
+                    loc[c] = ld_stream_f4(gl + j);
+                    cf[c] = ld_stream_f(p.confidences + row0 + j);
+                }
             }
         }
 #pragma unroll
@@ -372,7 +385,6 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                 l1[c] = 0.0f;
             }
         }
-        const float4 *gg = reinterpret_cast<const float4 *>(p.gt) + static_cast<size_t>(b) * M;
         for (int i = tid; i < n; i += T) {
             s.gt[i] = gg[i];
             s.u[i] = 0.0;
@@ -757,8 +769,15 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                 dc = __fdiv_rn(1.0f, arg);
             }
             if (logits) dc = __fmul_rn(dc, __fmul_rn(cf[c], __fsub_rn(1.0f, cf[c])));
-            if (p.d_loc) st_stream_f4(reinterpret_cast<float4 *>(p.d_loc) + row0 + j, dl);
-            if (p.d_conf) p.d_conf[row0 + j] = dc;
+            if (nheads > 1) {   // gradients in the per-head layouts too
+                int hh;
+                const size_t e = head_elem(sh_heads, nheads, j, b, hh);
+                if (sh_heads[hh].dloc) st_stream_f4(reinterpret_cast<float4 *>(sh_heads[hh].dloc) + e, dl);
+                if (sh_heads[hh].dconf) sh_heads[hh].dconf[e] = dc;
+            } else {
+                if (p.d_loc) st_stream_f4(reinterpret_cast<float4 *>(p.d_loc) + row0 + j, dl);
+                if (p.d_conf) p.d_conf[row0 + j] = dc;
+            }
         }
         if (p.stacked && !failed && crank == 0) {
             const int off = p.stk_offsets[b];
@@ -898,7 +917,7 @@ int launch_one(const MatchParams &p, cudaStream_t st) {
     MatchParams pp = p;
     if (CL == 1 && p.B > units && !(p.flags & MBX_FLAG_STATIC)) {
         // more images than resident CTAs: heavy-first order + dynamic scheduling
-        if (int e = launch_order(p.num_gt, p.B, p.M, p.order, st)) return e;
+        if (int e = launch_order(p.num_gt, p.gt_row, p.B, p.M, p.order, st)) return e;
         pp.dynamic = 1;
     }
     return check_cuda(cudaLaunchKernelEx(&cfg, kern, pp), "launch mbx_match_loss_reg_kernel");

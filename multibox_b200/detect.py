@@ -6,6 +6,8 @@ Arguments are CUDA ``torch.Tensor``s; all arithmetic runs in the sm_100a
 kernels behind the C ABI (``mbx_detect``, ``mbx_filter_proposals``,
 ``mbx_convert_proposals``).  There is no CPU path.
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -98,7 +100,7 @@ def postprocess(locs, confs, bbox_priors, restrictions=None, max_to_keep=None, o
     B, P = loc.shape[0], loc.shape[1]
     dev = loc.device
     conf = _f32c(confs, "confs").view(B, P)
-    pri = _f32c(bbox_priors, "bbox_priors")
+    pri = None if bbox_priors is None else _f32c(bbox_priors, "bbox_priors")   # None: locs are absolute boxes
     r = None if restrictions is None else _f32c(restrictions, "restrictions").view(B, 4)
     mk = None if max_to_keep is None else _i32c(max_to_keep, "max_to_keep").view(B)
     if k_max is None:
@@ -134,6 +136,53 @@ def postprocess(locs, confs, bbox_priors, restrictions=None, max_to_keep=None, o
                         _lib.ptr(boxes), _lib.ptr(pboxes), _lib.ptr(scores), _lib.ptr(idx), _lib.ptr(cnt),
                         None, 0, _stream(dev))
     _lib.check(rc, "mbx_detect")
+    return out
+
+
+def postprocess_heads(head_locations, head_confidences, bbox_priors, restrictions=None, max_to_keep=None,
+                      offsets=None, patch_dims=None, image_dims=None, is_flipped=None, nms_iou=None, k_max=None,
+                      logits=True, want_patch_boxes=True, warps=0):
+    """postprocess fed straight from the detection heads: `head_locations[h]`
+    / `head_confidences[h]` are the NHWC conv outputs of head h ([B,g,g,K*4] / [B,g,g,K], reference
+    model.py:213-293); the reshape + concat + sigmoid of model.py:295-322 happen inside the detect
+    kernel's load phase.  Same outputs as postprocess."""
+    from .loss import make_heads_struct
+    lib = _lib.load()
+    hl = [_f32c(t, "head_locations") for t in head_locations]
+    hc = [_f32c(t, "head_confidences") for t in head_confidences]
+    hs, B, P = make_heads_struct(hl, hc)
+    dev = hl[0].device
+    pri = _f32c(bbox_priors, "bbox_priors")
+    if pri.shape[0] != P:
+        raise ValueError("heads hold %d priors, bbox_priors %d" % (P, pri.shape[0]))
+    r = None if restrictions is None else _f32c(restrictions, "restrictions").view(B, 4)
+    mk = None if max_to_keep is None else _i32c(max_to_keep, "max_to_keep").view(B)
+    if k_max is None:
+        if mk is None:
+            raise ValueError("postprocess_heads needs k_max or max_to_keep")
+        k_max = int(mk.max().item())
+    k_max = max(1, min(int(k_max), 1024))
+    conv = [offsets, patch_dims, image_dims]
+    if any(c is not None for c in conv) and not all(c is not None for c in conv):
+        raise ValueError("offsets, patch_dims and image_dims must be given together")
+    off = None if offsets is None else _i32c(offsets, "offsets").view(B, 2)
+    pd = None if patch_dims is None else _i32c(patch_dims, "patch_dims").view(B, 2)
+    imd = None if image_dims is None else _i32c(image_dims, "image_dims").view(B, 2)
+    fl = None if is_flipped is None else _i32c(is_flipped, "is_flipped").view(B)
+    out = {"boxes": torch.empty((B, k_max, 4), dtype=torch.float64, device=dev),
+           "scores": torch.empty((B, k_max), dtype=torch.float32, device=dev),
+           "prior_idx": torch.empty((B, k_max), dtype=torch.int32, device=dev),
+           "count": torch.empty((B,), dtype=torch.int32, device=dev)}
+    pboxes = None
+    if want_patch_boxes:
+        pboxes = out["patch_boxes"] = torch.empty((B, k_max, 4), dtype=torch.float32, device=dev)
+    flags = (_lib.FLAG_LOGITS if logits else 0) | (int(warps) << _lib.FLAG_WARPS_SHIFT)
+    rc = lib.mbx_detect_heads(ctypes.byref(hs), _lib.ptr(pri), _lib.ptr(r), _lib.ptr(mk),
+                              _lib.ptr(off), _lib.ptr(pd), _lib.ptr(imd), _lib.ptr(fl),
+                              B, P, k_max, -1.0 if nms_iou is None else float(nms_iou), flags,
+                              _lib.ptr(out["boxes"]), _lib.ptr(pboxes), _lib.ptr(out["scores"]),
+                              _lib.ptr(out["prior_idx"]), _lib.ptr(out["count"]), None, 0, _stream(dev))
+    _lib.check(rc, "mbx_detect_heads")
     return out
 
 

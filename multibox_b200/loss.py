@@ -8,6 +8,8 @@ arithmetic runs in the hand-written sm_100a kernels behind the C ABI
 turns the device status word into the ``ValueError`` scipy would raise at
 reference loss.py:40.  There is no CPU path.
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -188,6 +190,206 @@ def add_loss_from_logits(locations, logits, batched_bboxes, batched_num_bboxes, 
     loc_loss, conf_loss, _ = _AddLoss.apply(locations, logits, batched_bboxes, batched_num_bboxes,
                                             bbox_priors, float(location_loss_alpha), _lib.FLAG_LOGITS,
                                             bool(validate))
+    return loc_loss, conf_loss
+
+
+def pad_ragged_gt(gt_flat, gt_row_offsets, max_num_bboxes):
+    """The padded block the reference's input pipeline builds (inputs.py:340-348): [B,M,4] zero
+    padded + counts [B].  Host/torch helper for tests and callers that need the padded form."""
+    off = gt_row_offsets.to(torch.int64)
+    B = off.numel() - 1
+    counts = (off[1:] - off[:-1]).to(torch.int32)
+    out = torch.zeros((B, int(max_num_bboxes), 4), dtype=torch.float32, device=gt_flat.device)
+    for b in range(B):
+        n = int(counts[b])
+        out[b, :n] = gt_flat[int(off[b]):int(off[b]) + n]
+    return out, counts
+
+
+def match_loss_ragged_raw(locations, confidences, gt_flat, gt_row_offsets, priors, alpha, max_num_bboxes,
+                          flags=0, want_mask=False, want_gt_idx=False, want_stacked=False, want_grads=True,
+                          out=None):
+    """``mbx_match_loss_ragged``: ground truth as CSR (gt_flat [N,4] f32, gt_row_offsets [B+1] int32)
+    instead of the zero-padded [B,M,4] block of reference inputs.py:340-348.  `max_num_bboxes` is
+    the per-image capacity M.  Same outputs as match_loss_raw."""
+    lib = _lib.load()
+    B, P = locations.shape[0], locations.shape[1]
+    M = int(max_num_bboxes)
+    dev = locations.device
+    out = {} if out is None else out
+
+    def buf(name, want, shape, dtype):
+        if not want:
+            return None
+        t = out.get(name)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            out[name] = t
+        return t
+
+    N = gt_flat.shape[0]
+    mask = buf("mask", want_mask, (B * P,), torch.int32)
+    gt_idx = buf("matched_gt_idx", want_gt_idx, (B * P,), torch.int32)
+    stacked = buf("stacked_gt", want_stacked, (max(N, 1), 4), torch.float32)
+    n_stacked = buf("n_stacked", want_stacked, (1,), torch.int32)
+    d_loc = buf("d_locations", want_grads, (B, P, 4), torch.float32)
+    d_conf = buf("d_confidences", want_grads, (B, P, 1), torch.float32)
+    results = buf("results", True, (_lib.RESULT_WORDS,), torch.float32)
+    ws = _workspace(dev, lib.mbx_match_workspace_bytes(B, P, M))
+    gt_arg = gt_flat if N > 0 else torch.zeros((1, 4), dtype=torch.float32, device=dev)
+    rc = lib.mbx_match_loss_ragged(_lib.ptr(locations), _lib.ptr(confidences), _lib.ptr(gt_arg),
+                                   _lib.ptr(gt_row_offsets), _lib.ptr(priors), B, P, M, float(alpha), int(flags),
+                                   _lib.ptr(mask), _lib.ptr(gt_idx), _lib.ptr(stacked), _lib.ptr(n_stacked),
+                                   _lib.ptr(d_loc), _lib.ptr(d_conf), None, _lib.ptr(results),
+                                   _lib.ptr(ws), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "mbx_match_loss_ragged")
+    return out
+
+
+class _AddLossRagged(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, locations, confidences, gt_flat, gt_row_offsets, bbox_priors, alpha, M, flags, validate):
+        loc = _f32c(locations, "locations")
+        B, P = loc.shape[0], loc.shape[1]
+        conf = _f32c(confidences, "confidences").view(B, P)
+        out = match_loss_ragged_raw(loc, conf, _f32c(gt_flat, "gt_flat"), _i32c(gt_row_offsets, "gt_row_offsets"),
+                                    _f32c(bbox_priors, "bbox_priors"), alpha, M, flags=flags)
+        res = out["results"]
+        if validate:
+            raise_for_status(res[2].item())
+        ctx.save_for_backward(out["d_locations"], out["d_confidences"])
+        ctx.conf_shape = confidences.shape
+        ctx.mark_non_differentiable(res)
+        return res[0], res[1], res
+
+    @staticmethod
+    def backward(ctx, g_loc, g_conf, _g_res):
+        d_loc, d_conf = ctx.saved_tensors
+        gl = d_loc * g_loc if g_loc is not None else None
+        gc = (d_conf * g_conf).view(ctx.conf_shape) if g_conf is not None else None
+        return gl, gc, None, None, None, None, None, None, None
+
+
+def add_loss_ragged(locations, confidences, gt_flat, gt_row_offsets, bbox_priors, location_loss_alpha,
+                    max_num_bboxes, validate=True, logits=False):
+    """add_loss (reference loss.py:55-117) with RAGGED ground truth: gt_flat [N,4] holds every
+    image's boxes back to back, gt_row_offsets [B+1] int32 the row range of each image -- the
+    format that replaces the MAX_NUM_BBOXES zero padding of reference inputs.py:340-348
+    (SURVEY.md section 8 f4).  Bit-identical to add_loss on the padded equivalent."""
+    loc_loss, conf_loss, _ = _AddLossRagged.apply(locations, confidences, gt_flat, gt_row_offsets, bbox_priors,
+                                                  float(location_loss_alpha), int(max_num_bboxes),
+                                                  _lib.FLAG_LOGITS if logits else 0, bool(validate))
+    return loc_loss, conf_loss
+
+
+# ----------------------------------------------------------------------------- head layout (model.py:295-322)
+def head_priors(num_bboxes_per_cell, grids=(8, 6, 4, 3, 2, 1)):
+    """Priors contributed by each detection head, in the reference's concatenation order
+    (model.py:314-320): g*g*K for the five grids, 1 for the 1x1 head (model.py:281-287)."""
+    return [g * g * (num_bboxes_per_cell if g > 1 else 1) for g in grids]
+
+
+def concat_heads(head_locations, head_confidences):
+    """The reference's own layout step (model.py:295-320, without the sigmoid): NHWC head outputs
+    [B,g,g,K*4] / [B,g,g,K] -> locations [B,P,4], confidences [B,P,1].  Plain torch; used by the
+    tests as the un-fused path the head-layout kernels must reproduce."""
+    B = head_locations[0].shape[0]
+    loc = torch.cat([t.reshape(B, -1) for t in head_locations], dim=1).reshape(B, -1, 4)
+    conf = torch.cat([t.reshape(B, -1) for t in head_confidences], dim=1).reshape(B, -1, 1)
+    return loc, conf
+
+
+def make_heads_struct(head_locations, head_confidences, d_locations=None, d_confidences=None):
+    """ctypes `mbx_heads` for a list of per-head CUDA tensors (kept alive by the caller)."""
+    hs = _lib.Heads()
+    n = len(head_locations)
+    if not 1 <= n <= _lib.MAX_HEADS or len(head_confidences) != n:
+        raise ValueError("need 1..%d heads, locations and confidences alike" % _lib.MAX_HEADS)
+    hs.num_heads = n
+    B = head_locations[0].shape[0]
+    P = 0
+    for k in range(n):
+        hl, hc = head_locations[k], head_confidences[k]
+        pri = hc.numel() // B
+        if hl.numel() != B * pri * 4:
+            raise ValueError("head %d: locations %s do not match confidences %s" % (k, tuple(hl.shape), tuple(hc.shape)))
+        hs.head_priors[k] = pri
+        hs.locations[k] = hl.data_ptr()
+        hs.confidences[k] = hc.data_ptr()
+        hs.d_locations[k] = d_locations[k].data_ptr() if d_locations is not None else None
+        hs.d_confidences[k] = d_confidences[k].data_ptr() if d_confidences is not None else None
+        P += pri
+    return hs, B, P
+
+
+def match_loss_heads_raw(head_locations, head_confidences, gt_bboxes, num_gt, priors, alpha, flags=0,
+                         gt_row_offsets=None, max_num_bboxes=None, want_mask=False, want_gt_idx=False,
+                         want_grads=True, want_conf_out=False):
+    """``mbx_match_loss_heads``: the training step fed from the per-head conv outputs.  Returns a dict
+    with per-head gradient lists ``d_head_locations`` / ``d_head_confidences`` (same shapes as the inputs)."""
+    lib = _lib.load()
+    hl = [_f32c(t, "head_locations") for t in head_locations]
+    hc = [_f32c(t, "head_confidences") for t in head_confidences]
+    dev = hl[0].device
+    dl = [torch.empty_like(t) for t in hl] if want_grads else None
+    dc = [torch.empty_like(t) for t in hc] if want_grads else None
+    hs, B, P = make_heads_struct(hl, hc, dl, dc)
+    if P != priors.shape[0]:
+        raise ValueError("heads hold %d priors, bbox_priors %d" % (P, priors.shape[0]))
+    M = int(max_num_bboxes) if gt_row_offsets is not None else gt_bboxes.shape[1]
+    out = {"d_head_locations": dl, "d_head_confidences": dc}
+    mask = torch.empty((B * P,), dtype=torch.int32, device=dev) if want_mask else None
+    gt_idx = torch.empty((B * P,), dtype=torch.int32, device=dev) if want_gt_idx else None
+    conf_out = torch.empty((B, P, 1), dtype=torch.float32, device=dev) if want_conf_out else None
+    results = torch.empty((_lib.RESULT_WORDS,), dtype=torch.float32, device=dev)
+    out.update(mask=mask, matched_gt_idx=gt_idx, confidences=conf_out, results=results)
+    ws = _workspace(dev, lib.mbx_match_workspace_bytes(B, P, M))
+    rc = lib.mbx_match_loss_heads(ctypes.byref(hs), _lib.ptr(gt_bboxes), _lib.ptr(num_gt), _lib.ptr(gt_row_offsets),
+                                  _lib.ptr(priors), B, P, M, float(alpha), int(flags),
+                                  _lib.ptr(mask), _lib.ptr(gt_idx), None, None, _lib.ptr(conf_out),
+                                  _lib.ptr(results), _lib.ptr(ws), ws.numel(),
+                                  torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "mbx_match_loss_heads")
+    return out
+
+
+class _AddLossHeads(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gt, num_gt, priors, alpha, flags, validate, nheads, *heads):
+        hl, hc = heads[:nheads], heads[nheads:]
+        out = match_loss_heads_raw(hl, hc, _f32c(gt, "batched_bboxes"), _i32c(num_gt, "batched_num_bboxes"),
+                                   _f32c(priors, "bbox_priors"), alpha, flags=flags)
+        res = out["results"]
+        if validate:
+            raise_for_status(res[2].item())
+        ctx.nheads = nheads
+        ctx.shapes = [t.shape for t in heads]
+        ctx.save_for_backward(*(out["d_head_locations"] + out["d_head_confidences"]))
+        ctx.mark_non_differentiable(res)
+        return res[0], res[1], res
+
+    @staticmethod
+    def backward(ctx, g_loc, g_conf, _g_res):
+        n = ctx.nheads
+        saved = ctx.saved_tensors
+        grads = []
+        for k, t in enumerate(saved):
+            g = g_loc if k < n else g_conf
+            grads.append((t * g).view(ctx.shapes[k]) if g is not None else None)
+        return (None, None, None, None, None, None, None) + tuple(grads)
+
+
+def add_loss_from_heads(head_locations, head_logits, batched_bboxes, batched_num_bboxes, bbox_priors,
+                        location_loss_alpha, validate=True, logits=True):
+    """add_loss fed straight from the detection heads: `head_locations[h]`
+    / `head_logits[h]` are the NHWC conv outputs of head h ([B,g,g,K*4] / [B,g,g,K], reference
+    model.py:213-293); the reshape + concat + sigmoid of model.py:295-322 happen inside the kernel
+    and the gradients come back per head, so the concatenated [B,P,5] tensor and its gradient are
+    never written to HBM.  With logits=False the confidences are taken as already-sigmoided."""
+    n = len(head_locations)
+    loc_loss, conf_loss, _ = _AddLossHeads.apply(batched_bboxes, batched_num_bboxes, bbox_priors,
+                                                 float(location_loss_alpha), _lib.FLAG_LOGITS if logits else 0,
+                                                 bool(validate), n, *(list(head_locations) + list(head_logits)))
     return loc_loss, conf_loss
 
 

@@ -123,3 +123,27 @@ def make_detect_inputs(K=5, B=256, keep=200, seed=0, nms_iou=0.5, patches=False)
                 max_to_keep=max_to_keep, offsets=offsets, patch_dims=patch_dims,
                 image_dims=image_dims, is_flipped=is_flipped,
                 image_ids=np.arange(B, dtype=np.int64), keep=keep, nms_iou=nms_iou)
+
+
+def split_heads(locations, confidences, K, grids=(8, 6, 4, 3, 2, 1)):
+    """Inverse of the reference's layout step (model.py:295-320): cut concatenated [B,P,4] /
+    [B,P,1] arrays back into the per-head NHWC conv outputs [B,g,g,K*4] / [B,g,g,K] they would
+    have been concatenated from (the 1x1 head has a single box, model.py:281-287)."""
+    B = locations.shape[0]
+    hl, hc, off = [], [], 0
+    for g in grids:
+        k = K if g > 1 else 1
+        n = g * g * k
+        hl.append(np.ascontiguousarray(locations[:, off:off + n].reshape(B, g, g, k * 4)))
+        hc.append(np.ascontiguousarray(confidences[:, off:off + n].reshape(B, g, g, k)))
+        off += n
+    assert off == locations.shape[1]
+    return hl, hc
+
+
+def ragged_gt(gt, num_gt):
+    """Padded [B,M,4] + counts -> (gt_flat [N,4], gt_row_offsets [B+1] int32)."""
+    off = np.zeros(len(num_gt) + 1, dtype=np.int32)
+    off[1:] = np.cumsum(num_gt)
+    flat = np.concatenate([gt[b, :num_gt[b]] for b in range(len(num_gt))] + [np.zeros((0, 4), np.float32)], axis=0)
+    return np.ascontiguousarray(flat.astype(np.float32)), off

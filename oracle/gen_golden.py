@@ -17,6 +17,7 @@ Fixtures
   match_cfg2.npz     BASELINE configs[1] inputs, reference mask / stacked GT
   detect_small.npz   detect loop body on B=12 mixed patches (whole / crop / flip)
   detect_cfg3_head.npz  first 16 images of configs[2] (no NMS: reference has none)
+  patches.npz        extract_patches geometry (detect.py:20-72) for six image / crop shapes
 """
 import argparse
 import hashlib
@@ -158,6 +159,26 @@ def gen_detect():
     print("detect_cfg3_head.npz rows =", len(ids))
 
 
+PATCH_CASES = [(600, 800, (299, 299), (113, 113)), (299, 299, (299, 299), (113, 113)),
+               (480, 640, (185, 185), (69, 69)), (200, 500, (299, 299), (113, 113)),
+               (525, 412, (185, 185), (69, 69)), (299, 412, (299, 299), (113, 113))]   # == tests/test_patches.py CASES
+
+
+def gen_patches():
+    """patches.npz: the reference's own extract_patches (detect.py:20-72) on all-zero images."""
+    from multibox_b200 import patches
+    ref = ref_slices.load()["extract_patches"]
+    out = {}
+    for i, (h, w, dims, strides) in enumerate(PATCH_CASES):
+        _, off, restr, n = ref(np.zeros((h, w, 3), np.float32), dims, strides)
+        o2, r2, n2 = patches.extract_patches(h, w, dims, strides)
+        assert int(n) == int(n2) and np.array_equal(off, o2) and np.array_equal(restr, r2)
+        out["off_%d" % i] = off
+        out["restr_%d" % i] = restr
+    np.savez_compressed(os.path.join(GOLD, "patches.npz"), **out)
+    print("patches.npz cases =", len(PATCH_CASES))
+
+
 def check_nplog(exhaustive):
     step = 1 if exhaustive else 101
     bad = 0
@@ -178,6 +199,7 @@ def main():
     gen_priors()
     gen_match()
     gen_detect()
+    gen_patches()
 
 
 if __name__ == "__main__":

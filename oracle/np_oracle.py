@@ -319,3 +319,48 @@ def eval_topk(locs, confs, bbox_priors, input_size, image_ids, k=100):
             x1, y1, x2, y2 = sb[t]
             rows.append([int(image_ids[b]), x1, y1, x2 - x1, y2 - y1, float(sc[t].reshape(-1)[0]), 1])
     return rows
+
+
+# ----------------------------------------------------------------------------- layout steps either side of the path
+def concat_heads(head_locations, head_confidences):
+    """reference model.py:295-320 (without the sigmoid of :322): per-head NHWC outputs
+    [B,g,g,K*4] / [B,g,g,K] are flattened per image and concatenated in head order, then viewed
+    as [B,P,4] / [B,P,1].  This fixes the prior order the priors of priors.py:185-314 follow."""
+    B = head_locations[0].shape[0]
+    loc = np.concatenate([np.reshape(t, (B, -1)) for t in head_locations], axis=1)
+    conf = np.concatenate([np.reshape(t, (B, -1)) for t in head_confidences], axis=1)
+    return np.reshape(loc, (B, -1, 4)), np.reshape(conf, (B, -1, 1))
+
+
+def pad_ragged_gt(gt_flat, gt_row_offsets, max_num_bboxes):
+    """reference inputs.py:340-348: every image's boxes zero-padded to MAX_NUM_BBOXES rows."""
+    B = len(gt_row_offsets) - 1
+    gt = np.zeros((B, max_num_bboxes, 4), dtype=np.float32)
+    num = np.zeros((B,), dtype=np.int32)
+    for b in range(B):
+        lo, hi = int(gt_row_offsets[b]), int(gt_row_offsets[b + 1])
+        num[b] = hi - lo
+        gt[b, :hi - lo] = gt_flat[lo:hi]
+    return gt, num
+
+
+def merge_patches(per_patch, image_index, num_images, nms_iou=0.5, max_detections=200):
+    """PROJECT SPECIFICATION (no reference counterpart; parity unpinned): what
+    multibox_b200.patches.merge_patches computes.  per_patch = the list postprocess() returns
+    (one dict per patch: boxes f64 [c,4] in image coordinates, scores f32 [c]).  Per image: pool the
+    detections of its patches in (patch order, rank) order, stable-argsort-then-reverse by score
+    (ties: later candidate first), keep the top max_detections, greedy NMS on the float32 boxes."""
+    out = []
+    for i in range(num_images):
+        pats = [b for b in range(len(per_patch)) if image_index[b] == i]
+        boxes = np.concatenate([per_patch[b]["boxes"].reshape(-1, 4) for b in pats] + [np.zeros((0, 4))], 0)
+        scores = np.concatenate([per_patch[b]["scores"].reshape(-1) for b in pats] + [np.zeros((0,), np.float32)], 0)
+        src = np.concatenate([np.full(per_patch[b]["scores"].reshape(-1).shape[0], b, np.int32) for b in pats] +
+                             [np.zeros((0,), np.int32)], 0)
+        order = np.argsort(scores.astype(np.float32), kind="stable")[::-1][:max_detections]
+        boxes, scores, src = boxes[order], scores[order], src[order]
+        if nms_iou is not None and len(order):
+            keep = greedy_nms(boxes.astype(np.float32), nms_iou)
+            boxes, scores, src = boxes[keep], scores[keep], src[keep]
+        out.append(dict(boxes=boxes, scores=scores.astype(np.float32), source_patch=src))
+    return out

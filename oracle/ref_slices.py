@@ -15,6 +15,7 @@ Slices:
   * loss.py:6-53        compute_assignments        -- one shim: the Python-2
                         integer division at loss.py:16 becomes ``//``
   * detect.py:74-131    filter_proposals / convert_proposals -- verbatim
+  * detect.py:20-72     extract_patches (patch geometry; called with an all-zero image) -- verbatim
 The inline loop body detect.py:408-436 is not a function; its statement order
 is followed by ``detect_loop_body`` below, calling the verbatim functions, with
 ``np.asscalar`` -> ``.item()`` and ``np.argsort(kind='stable')`` pinned (numpy's
@@ -53,8 +54,9 @@ def load():
     src = src.replace(shim_from, "num_predictions = locations.shape[0] // batch_size")
     exec(compile(src, "ref:loss.py:6-53(+//)", "exec"), ns)
     exec(compile(_slice("detect.py", 74, 131), "ref:detect.py:74-131", "exec"), ns)
+    exec(compile(_slice("detect.py", 20, 72), "ref:detect.py:20-72", "exec"), ns)
     for k in ("generate_priors", "compute_assignments", "filter_proposals",
-              "convert_proposals", "SMALL_EPSILON"):
+              "convert_proposals", "extract_patches", "SMALL_EPSILON"):
         _cache[k] = ns[k]
     return _cache
 
