@@ -13,7 +13,8 @@ grouping by image and the removal of cross-patch duplicates to whoever reads
 ``results-dense-*.json`` (detect.py:438-460).  ``merge_patches`` does that step on the GPU with
 the same detect kernel (zero priors: decode is the identity): per image, the detections of all of
 its patches are pooled, sorted by score and put through greedy NMS.  Like the in-patch NMS this
-is an extension with no reference counterpart (parity unpinned; oracle = np_oracle.merge_patches).
+is an extension with no reference counterpart (parity unpinned; its specification is restated for
+the tests next to the in-patch NMS one).
 """
 import numpy as np
 import torch
