@@ -79,8 +79,12 @@ __device__ __forceinline__ bool iou_fast(float4 a, float area_a, float4 b, float
     // den <= 0 needs no second look either (inter >= 0, thr > 0): den < 0 (a box with x2 < x1 -- the
     // reference applies no validity fix-up, detect.py:412-413) gives a quotient <= 0, never > thr;
     // den == 0 gives t = 0, d = inter, and inter/0 > thr <=> inter > 0.
-    near = (den > 0.0f) && (!(den >= 1e-20f) || !(fabsf(d) > __fmul_rn(9.5367431640625e-07f, t)));
-    return (d > 0.0f) && (den >= 0.0f);
+    // (every operand is computed before the predicates are combined, so that the combination is
+    // pure predicate logic: a short-circuit around arithmetic makes the compiler branch per pair)
+    const float tolt = __fmul_rn(9.5367431640625e-07f, t);
+    const bool pos = den > 0.0f, normal = den >= 1e-20f, clear = fabsf(d) > tolt, nonneg = den >= 0.0f, gt = d > 0.0f;
+    near = pos && !(normal && clear);
+    return gt && nonneg;
 }
 __device__ __noinline__ bool iou_exact(float4 a, float area_a, float4 b, float area_b, float thr) {
     const float w = fmaxf(0.0f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
@@ -440,7 +444,7 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
                 bool any_near = !thr_ok && jvalid;
 #pragma unroll
                 for (int u = 0; u < RU; ++u) {
-                    const bool act = jvalid && lane > ib + u;   // j > i (and so i < kk, since j < kk)
+                    const bool act = jvalid && (lane > ib + u);   // j > i (and so i < kk, since j < kk)
                     bool nr;
                     const bool sp = iou_fast(rbox[u], rarea[u], bj, aj, p.nms_iou, nr);
                     bal[u] = __ballot_sync(0xffffffffu, sp && act);
@@ -483,9 +487,11 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
                     s.klist[lane] = lane < nk ? (c << 5) + static_cast<int>(__fns(kept, 0, lane + 1)) : -1;
                     if (lane == 0) s.cnt[3] = nk;
                 }
+                MBX_DT(5);   // (timing builds) serial resolve
                 const int nwords = W - 1 - c;
                 if (nwords == 0) break;
                 __syncthreads();
+                MBX_DT(6);   // (timing builds) wait for the resolve
                 // ---- the kept boxes of chunk c against the later chunks.  A lane owns NC boxes (one in
                 // each of NC later chunks: the row broadcast and its bookkeeping are shared by NC
                 // decisions); the warps split the work by (group of NC chunks, slice of the kept rows)
@@ -553,6 +559,7 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
                     cross(std::integral_constant<int, 2>{});
                 else
                     cross(std::integral_constant<int, 1>{});
+                MBX_DT(7);   // (timing builds) cross-chunk suppression
                 __syncthreads();   // remw[c+1..] complete before the next chunk is resolved
             }
             if (warp == 0) {

@@ -44,7 +44,8 @@ def dev(a):
 
 if detect_mode:
     from multibox_b200 import detect
-    dn = ["load/decode/keys", "select + sort", "NMS: chunk triangles", "NMS: resolve + cross-chunk", "store"]
+    dn = ["load/decode/keys", "select + sort", "NMS: chunk triangles", "NMS: barrier waits (rest)", "store",
+          "NMS: serial resolve", "NMS: wait for resolve", "NMS: cross-chunk"]
     for label, kw in (("cfg3", dict(K=5, B=148, keep=200, seed=1003)), ("K=11", dict(K=11, B=148, keep=200, seed=4))):
         q = synth.make_detect_inputs(**kw)
         B = q["B"]
