@@ -62,6 +62,9 @@ extern "C" {
                                        PREVIOUS step's reduction (no waiting for slower peers) */
 #define MBX_FLAG_STATIC        16u  /* keep the static image -> CTA assignment even when the batch exceeds
                                        the resident CTAs (default then: heavy-first dynamic scheduling) */
+#define MBX_FLAG_HOST_RESULTS  32u  /* `results` is mapped pinned HOST memory that the caller polls: the
+                                       launch sequence word results[15] is published after a system-scope
+                                       fence (costs ~1 us; without the flag word 15 is still written last) */
 #define MBX_FLAG_GENERIC       4u   /* force the generic shared-memory matching kernel (any P) instead
                                        of the register-resident family (tuning / testing) */
 #define MBX_FLAG_WARPS_SHIFT   8    /* bits 8..15: force CTA size in warps (0 = heuristic) */
@@ -114,6 +117,10 @@ size_t mbx_match_workspace_bytes(int B, int P, int M);
  *                           mbx_match_loss_allreduce is used with world > 1),
  *                           [12],[13] the same as float32, [14] the step index the
  *                           global sums belong to
+ *                           [15] launch sequence number (uint32 bits, never 0), stored last;
+ *                           with MBX_FLAG_HOST_RESULTS after a system-scope fence, so that a
+ *                           caller that passed mapped pinned HOST memory as `results` may poll
+ *                           it instead of synchronising the stream
  *   n_stacked       [1]     int32 number of rows written to stacked_gt
  * The status word is also OR-ed into results[2]; it is 0 when every image was
  * solved.  grads/loss outputs are produced iff `results` is non-NULL.

@@ -407,7 +407,8 @@ class MultiboxLossStep:
     """
 
     def __init__(self, B, P, M, priors, alpha, device="cuda", logits=False, want_mask=False,
-                 want_stacked=False, warps=0, use_graph=False, peer=None, deferred_allreduce=False):
+                 want_stacked=False, warps=0, use_graph=False, peer=None, deferred_allreduce=False,
+                 host_results=False):
         self.B, self.P, self.M, self.alpha = B, P, M, float(alpha)
         self.device = torch.device(device)
         if self.device.index is None:
@@ -438,6 +439,16 @@ class MultiboxLossStep:
         self.use_graph = bool(use_graph)
         self._graph = None
         self._launch = None
+        # host_results: the kernel stores the 64-byte result block straight into mapped pinned host
+        # memory and the host polls the launch sequence word (results[15]) -- no D2H copy node, no
+        # stream synchronisation on the step's critical path.  Host-buffer path only.
+        self.host_results = bool(host_results) and self.peer is None
+        if self.host_results:
+            self.flags |= _lib.FLAG_HOST_RESULTS
+            self.out["results"] = self.h_res
+            self._res_u32 = self.h_res.numpy().view("uint32")
+            self._res_f32 = self.h_res.numpy()
+            self._res_u32[15] = 0
 
     def _views(self, buf):
         (a0, n0), (a1, n1), (a2, n2), (a3, n3) = self._sections
@@ -486,7 +497,22 @@ class MultiboxLossStep:
     def _enqueue_host_step(self):
         self.d_in.copy_(self.h_in, non_blocking=True)           # one H2D copy of the packed inputs
         self._launch()                                           # one kernel
-        self.h_res.copy_(self.out["results"], non_blocking=True)  # losses + status (32 bytes)
+        if not self.host_results:
+            self.h_res.copy_(self.out["results"], non_blocking=True)  # losses + status (64 bytes)
+
+    def _wait_host_results(self):
+        """Spins on the launch sequence word the kernel stores last into the mapped result block."""
+        import time
+        u = self._res_u32
+        spins = 0
+        while u[15] == 0:
+            spins += 1
+            if spins & 0xffff == 0 and spins > (1 << 22):
+                t0 = time.perf_counter()
+                torch.cuda.current_stream(self.device).synchronize()    # something is wrong: fall back
+                if u[15] == 0:
+                    raise RuntimeError("MultiboxLossStep: the kernel finished without publishing its results "
+                                       "(%.3f s)" % (time.perf_counter() - t0))
 
     def _ensure_ready(self):
         if self._launch is None:
@@ -553,10 +579,18 @@ class MultiboxLossStep:
                 if validate:
                     raise_for_status(self.h_res[2].item())
                 return float(self.h_res[0]), float(self.h_res[1])
+        if self.host_results:
+            self._res_u32[15] = 0
         if self._graph is not None:
             self._graph.replay()
         else:
             self._enqueue_host_step()
+        if self.host_results:
+            self._wait_host_results()
+            r = self._res_f32
+            if validate and r[2] != 0.0:
+                raise_for_status(float(r[2]))
+            return float(r[0]), float(r[1])
         torch.cuda.current_stream(self.device).synchronize()
         if validate:
             raise_for_status(self.h_res[2].item())

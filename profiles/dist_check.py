@@ -44,6 +44,28 @@ for deferred in (False, True):
     if rank == 0:
         print("dist_check world=%d deferred=%s: fused global losses %.6f %.6f  oracle %.6f %.6f  -> %s"
               % (world, deferred, gl, gc, ref["location_loss_f64"], ref["confidence_loss_f64"], "OK" if ok else "MISMATCH"))
+# a shard larger than the resident CTAs: heavy-first dynamic scheduling + the deferred poster CTA
+Bbig = 700 * world
+dbig = synth.make_train_inputs(K=7, B=Bbig, M=100, dist="coco_person", seed=99)
+lo, hi = mdist.shard_range(Bbig)
+shb = mdist.shard_batch({k: dbig[k] for k in ("locations", "confidences", "gt", "num_gt")}, Bbig)
+for deferred in (False, True):
+    step = loss.MultiboxLossStep(hi - lo, dbig["P"], 100, dbig["priors"], dbig["alpha"], peer=peer, use_graph=True,
+                                 deferred_allreduce=deferred)
+    for it in range(4):
+        step.step_host(shb["locations"], shb["confidences"], shb["gt"], shb["num_gt"])
+    t64 = step.out["results"][4:8].view(torch.float64).clone()
+    dist.all_reduce(t64)
+    gl, gc = step.flush() if deferred else step.global_losses()
+    okb = abs(gl - t64[0].item()) <= 1e-12 * abs(gl) and abs(gc - t64[1].item()) <= 1e-12 * abs(gc)
+    solo = loss.MultiboxLossStep(hi - lo, dbig["P"], 100, dbig["priors"], dbig["alpha"], use_graph=False)
+    l1, c1 = solo.step_host(shb["locations"], shb["confidences"], shb["gt"], shb["num_gt"])
+    l2 = step.out["results"][0].item()
+    okb &= (l1 == l2)
+    ok &= okb
+    if rank == 0:
+        print("dist_check world=%d big shard (%d images/rank) deferred=%s: %.4f %.4f -> %s"
+              % (world, hi - lo, deferred, gl, gc, "OK" if okb else "MISMATCH"))
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.barrier()

@@ -69,29 +69,45 @@ for label, d in (("cfg2", synth.make_train_inputs(**synth.TRAIN_CONFIGS["cfg2"])
     B, P = d["B"], d["P"]
     cl = int(os.environ.get("MBX_CLUSTER", "1"))
     for w in ([warps] if warps else [4, 8, 16]):
-        out = {"mask": torch.zeros(max(B * P, B * 16 * 8 * 2 * 4 + 64), dtype=torch.int32, device="cuda")}
-        for _ in range(2):
+        out = {"mask": torch.zeros(max(B * P, B * 16 * 10 * 2 * 4 + 64), dtype=torch.int32, device="cuda")}
+        evs = []
+        for _ in range(3):
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
             loss.match_loss_raw(dev(d["locations"]), dev(d["confidences"]).view(B, P), dev(d["gt"]), dev(d["num_gt"]),
                                 dev(d["priors"]), d["alpha"], want_mask=True, warps=w, cluster=cl, out=out)
+            b_.record()
+            evs.append((a, b_))
         torch.cuda.synchronize()
-        t = out["mask"].cpu().numpy().view(np.int64)[:B * cl * w * 8].reshape(B, cl * w, 8)
+        t = out["mask"].cpu().numpy().view(np.int64)[:B * cl * w * 10].reshape(B, cl * w, 10)
         b = int(np.argmax(d["num_gt"]))      # grid == B*cl here: cluster b solves image b
         print("%s warps=%d cluster=%d: image %d (n=%d) per-warp mean cycles by phase" % (label, w, cl, b, d["num_gt"][b]))
-        tot = t[b].mean(0)
+        tot = t[b, :, :8].mean(0)
         for k, nm in enumerate(names):
             print("   %-16s %9.0f  (%.0f per augmentation)" % (nm, tot[k], tot[k] / max(1, d["num_gt"][b])))
-        print("   total %.0f cycles; slowest warp %.0f" % (tot.sum(), t[b].sum(1).max()))
+        print("   total %.0f cycles; slowest warp %.0f" % (tot.sum(), t[b, :, :8].sum(1).max()))
+        # kernel-level timeline from %globaltimer (ns): when each CTA started / finished
+        g0, g1 = t[:, :, 8], t[:, :, 9]
+        k0 = g0.min()
+        cyc = t[:, :, :8].sum(2).max(1)
+        slow = int(np.argmax(g1.max(1)))
+        print("   timeline (ns after the first CTA started): CTA starts %d..%d, CTA ends %d..%d (last: image %d, n=%d, "
+              "%d cycles); event time of the launch %.1f us" %
+              (g0.min() - k0, g0.max() - k0, g1.max(1).min() - k0, g1.max() - k0, slow, d["num_gt"][slow], cyc[slow],
+               evs[-1][0].elapsed_time(evs[-1][1]) * 1e3))
+        order = np.argsort(-cyc)[:5]
+        print("   slowest images: " + ", ".join("img %d n=%d %d cyc" % (i, d["num_gt"][i], cyc[i]) for i in order))
 
 # COCO-person-shaped images (K=7, P=904, M=100): the per-image fixed costs at small GT counts
 d = synth.make_train_inputs(K=7, B=148, M=100, dist="coco_person", seed=1004)
 B, P = d["B"], d["P"]
 for w in ([warps] if warps else [8]):
-    out = {"mask": torch.zeros(max(B * P, B * 16 * 8 * 2 * 4 + 64), dtype=torch.int32, device="cuda")}
+    out = {"mask": torch.zeros(max(B * P, B * 16 * 10 * 2 * 4 + 64), dtype=torch.int32, device="cuda")}
     for _ in range(2):
         loss.match_loss_raw(dev(d["locations"]), dev(d["confidences"]).view(B, P), dev(d["gt"]), dev(d["num_gt"]),
                             dev(d["priors"]), d["alpha"], want_mask=True, warps=w, out=out)
     torch.cuda.synchronize()
-    t = out["mask"].cpu().numpy().view(np.int64)[:B * w * 8].reshape(B, w, 8)
+    t = out["mask"].cpu().numpy().view(np.int64)[:B * w * 10].reshape(B, w, 10)[:, :, :8]
     for want in (0, 3, 8, int(d["num_gt"].max())):
         sel = np.where(d["num_gt"] == want)[0]
         if len(sel) == 0:
