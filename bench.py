@@ -451,13 +451,10 @@ def main():
                                                     "finds its inputs in L2" % tr["nsets"]),
         "e2e": {"value": world * B * args.steps / e2e_sec, "unit": "images/s",
                 "h2d_bytes_per_step": tr["h2d"], "d2h_bytes_per_step": tr["d2h"],
-                "how": ("MultiboxLossStep.step_pinned(use_graph=True, host_results=True): one CUDA-graph launch = 1 "
-                        "packed pinned H2D copy + 1 kernel that stores the 64-byte loss/status block straight into "
-                        "mapped pinned host memory; the host polls the launch sequence word and checks the status, "
-                        "every step; wall clock") if world == 1 else
-                       ("MultiboxLossStep.step_pinned(use_graph=True): one CUDA-graph launch = 1 packed pinned H2D "
-                        "copy + 1 kernel (+ fused all-reduce) + D2H of losses/status, then stream sync and status "
-                        "check, every step; wall clock")},
+                "how": "MultiboxLossStep.step_pinned(use_graph=True, host_results=True): one CUDA-graph launch = 1 "
+                       "packed pinned H2D copy + 1 kernel (with the loss all-reduce fused in when N > 1) that stores "
+                       "the 64-byte loss/status block straight into mapped pinned host memory; the host polls the "
+                       "launch sequence word and checks the status, every step; wall clock"},
         "gpu_launches": tr["launches_per_step"] * args.steps,
         "collective": ("loss SUM all-reduce fused into the kernel (NVLink peer stores + system-scope arrival "
                        "counters, 4-deep slot ring); step k posts its sums and completes step k-1's reduction, the "

@@ -442,7 +442,7 @@ class MultiboxLossStep:
         # host_results: the kernel stores the 64-byte result block straight into mapped pinned host
         # memory and the host polls the launch sequence word (results[15]) -- no D2H copy node, no
         # stream synchronisation on the step's critical path.  Host-buffer path only.
-        self.host_results = bool(host_results) and self.peer is None
+        self.host_results = bool(host_results)
         if self.host_results:
             self.flags |= _lib.FLAG_HOST_RESULTS
             self.out["results"] = self.h_res
@@ -549,7 +549,8 @@ class MultiboxLossStep:
                                      self.peer.world, self.peer.rank,
                                      torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(rc, "mbx_allreduce_flush")
-        self.h_res.copy_(self.out["results"], non_blocking=True)
+        if self.out["results"] is not self.h_res:
+            self.h_res.copy_(self.out["results"], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         raise_for_status(self.h_res[2].item())
         return self.global_losses()

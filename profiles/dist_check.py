@@ -51,10 +51,10 @@ lo, hi = mdist.shard_range(Bbig)
 shb = mdist.shard_batch({k: dbig[k] for k in ("locations", "confidences", "gt", "num_gt")}, Bbig)
 for deferred in (False, True):
     step = loss.MultiboxLossStep(hi - lo, dbig["P"], 100, dbig["priors"], dbig["alpha"], peer=peer, use_graph=True,
-                                 deferred_allreduce=deferred)
+                                 deferred_allreduce=deferred, host_results=True)
     for it in range(4):
         step.step_host(shb["locations"], shb["confidences"], shb["gt"], shb["num_gt"])
-    t64 = step.out["results"][4:8].view(torch.float64).clone()
+    t64 = step.out["results"][4:8].view(torch.float64).clone().cuda()    # (the result block lives in pinned host memory)
     dist.all_reduce(t64)
     gl, gc = step.flush() if deferred else step.global_losses()
     okb = abs(gl - t64[0].item()) <= 1e-12 * abs(gl) and abs(gc - t64[1].item()) <= 1e-12 * abs(gc)
