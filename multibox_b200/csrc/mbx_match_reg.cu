@@ -41,6 +41,22 @@ int launch_match_reg(const MatchParams &p, int force_warps, int force_cols, int 
     // remote stores eat what the split first-step pass saves: profiles/README.md), so it is only
     // used when forced through MBX_FLAG_CLUSTER_SHIFT.
     int cl = force_cluster ? force_cluster : 1;
+    // Row split (two warp groups per image, each holding every column; the batched first step is
+    // shared by rows), for shapes where a 256- or 128-thread group covers the priors with <= 3
+    // columns per thread.  Implemented and parity-tested (bit-identical), but on B200 it measured
+    // SLOWER than one group even at B = 32 (22.0 vs 20.5 us per launch on configs[1]: the redundant
+    // loads / logs of the helper group and the 16-warp barriers cost more than the halved first step
+    // saves), so it is only used when forced with MBX_FLAG_ROWSPLIT.
+    const bool want_split = (p.flags & MBX_FLAG_ROWSPLIT) != 0 && !(p.flags & MBX_FLAG_NO_ROWSPLIT);
+    if (want_split && cl == 1) {
+        const int gw = force_warps ? force_warps / 2 : (p.P <= 384 ? 4 : 8);      // warps of one group
+        const int cols = force_cols ? force_cols : (p.P + gw * 32 - 1) / (gw * 32);
+        if ((gw == 4 || gw == 8) && cols >= 1 && cols <= 3 && cols * gw * 32 >= p.P) {
+            const int rc = dispatch(p, 2 * gw, cols, -1, st);
+            if (rc != MBX_E_TOO_LARGE) return rc;
+        }
+        if (p.flags & MBX_FLAG_ROWSPLIT) return MBX_E_TOO_LARGE;
+    }
     if (cl > 1) {
         const int tc = nwarps * 32 * cl;
         const int cols = force_cols ? force_cols : (p.P + tc - 1) / tc;

@@ -227,14 +227,23 @@ constexpr int min_blocks_per_sm() {
 // REPLICATED in each CTA's shared memory; whoever updates them stores to all replicas through
 // distributed shared memory, and cluster barriers replace the CTA barriers where such updates
 // must be visible.  Per-row first-step minima and the dirty marks live in the leader (rank 0).
-template <int NWARPS, int C, int CL>
-__global__ void __launch_bounds__(NWARPS * 32, CL > 1 ? 1 : min_blocks_per_sm<NWARPS, C>())
+//
+// RSP > 1 (row split; CL == 1): the CTA holds RSP warp GROUPS that each own ALL the columns (thread
+// `ctid` of every group holds the same C columns, loads and logs computed redundantly).  The groups
+// share the batched first step by ROWS -- the longest phase of a latency-bound image is cut by RSP
+// -- after which only group 0 carries column state; the helper groups take part in the barriers and
+// block-wide reductions with empty candidates.  Chosen when every image has an SM to itself.
+template <int NWARPS, int C, int CL, int RSP>
+__global__ void __launch_bounds__(NWARPS * 32, (CL > 1 || RSP > 1) ? 1 : min_blocks_per_sm<NWARPS, C>())
 mbx_match_loss_reg_kernel(const MatchParams p) {
     namespace cg = cooperative_groups;
     constexpr int T = NWARPS * 32;
-    constexpr int TC = T * CL;        // column stride of a thread
+    constexpr int TG = T / RSP;       // threads of one column group
+    constexpr int TC = TG * CL;       // column stride of a thread
     constexpr int NPART = NWARPS * CL;   // warps per image
+    constexpr int NPG = NPART / RSP;     // warps that share one row of the batched first step
     static_assert(NPART <= 32, "one lane per warp partial");
+    static_assert(RSP == 1 || (CL == 1 && NWARPS % RSP == 0), "row split: single CTA, whole warp groups");
     constexpr bool RS = (C <= 3);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RSmem s;
@@ -245,7 +254,9 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int crank = 0;
     if constexpr (CL > 1) crank = static_cast<int>(cg::this_cluster().block_rank());
-    const int gtid = crank * T + tid;   // thread index within the image's cluster
+    const int rgrp = (RSP > 1) ? tid / TG : 0;           // warp group (row split)
+    const bool helper = RSP > 1 && rgrp != 0;            // holds columns for the first step only
+    const int gtid = crank * TG + (RSP > 1 ? tid % TG : tid);   // column-owner index within the image's cluster
     const int gwarp = crank * NWARPS + warp;
     // barrier over every thread working on the image
     auto image_sync = [&]() {
@@ -299,10 +310,10 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_g0));
 #endif
 
-    unsigned invalid_mask = 0;   // columns of this thread beyond P
+    unsigned invalid_mask = 0;   // columns of this thread beyond P (helper groups: all, for the general search)
 #pragma unroll
     for (int c = 0; c < C; ++c)
-        if (gtid + c * TC >= P) invalid_mask |= 1u << c;
+        if (helper || gtid + c * TC >= P) invalid_mask |= 1u << c;
 
     // Deferred fused all-reduce: the launch appends one extra CTA that only sends the previous
     // step's loss sums to the peers (NVLink latency overlaps this kernel's work).
@@ -374,7 +385,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                 }
                 if (logits) {
                     cf[c] = sigmoidf_(cf[c]);              // model.py:322
-                    if (p.conf_out) p.conf_out[row0 + j] = cf[c];
+                    if (p.conf_out && !helper) p.conf_out[row0 + j] = cf[c];
                 }
                 const float ce = boundary ? cf[c] : __fadd_rn(cf[c], kEps32);   // loss.py:74
                 lc[c] = nplogf(ce);                                              // loss.py:21
@@ -410,7 +421,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
         // RB*C independent cost chains per thread.  fp32 keys are exact here (r == C).
         {
             constexpr int RB = (C <= 2) ? 4 : ((C <= 3) ? 3 : 2);
-            for (int i0 = 0; i0 < n; i0 += RB) {
+            for (int i0 = rgrp * RB; i0 < n; i0 += RB * RSP) {
                 float4 g[RB];
                 float best[RB];
                 unsigned bcol[RB], btie[RB];
@@ -442,18 +453,18 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                     warp_rowmin(key, col, tieb);
                     if (lane == 0 && i0 + r < n) {
                         const uint2 e = make_uint2(key, col | (tieb ? 0x80000000u : 0u));
-                        if (NPART > 1)
-                            store_leader(&s.rowpart[(i0 + r) * NPART + gwarp], e);
+                        if (NPG > 1)
+                            store_leader(&s.rowpart[(i0 + r) * NPG + gwarp % NPG], e);
                         else
                             s.rowmin[i0 + r] = e;
                     }
                 }
             }
-            if (NPART > 1) {
+            if (NPG > 1) {
                 image_sync();
                 for (int i = warp; i < n && crank == 0; i += NWARPS) {
                     uint2 e = make_uint2(0xffffffffu, kColNone);
-                    if (lane < NPART) e = s.rowpart[i * NPART + lane];
+                    if (lane < NPG) e = s.rowpart[i * NPG + lane];
                     unsigned key = e.x, col = e.y & kColNone;
                     bool tieb = (e.y >> 31) != 0u;
                     warp_rowmin(key, col, tieb);
@@ -522,7 +533,9 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                 const float4 g = s.gt[i];
                 unsigned long long key;
                 unsigned bj = kPayNone, tie = 0u;
-                if (R == 0) {
+                if (helper) {
+                    key = ~0ull;   // a helper group has no column in the search: empty candidate
+                } else if (R == 0) {
                     // First Dijkstra step: min_val = 0, u[cur] = 0, nothing scanned, so
                     // r = (0 + C) - 0 - v = C - v.  Where v == 0 (every column that was never
                     // passed through by an augmenting path) r is the fp32 cost itself, and fp32
@@ -651,7 +664,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                     is_sink = !(k & 1u);
                 }
                 const int cstar = jstar / TC;
-                const bool owner = (jstar - cstar * TC) == gtid;
+                const bool owner = !helper && (jstar - cstar * TC) == gtid;
                 if (is_sink) {
                     if (owner) {
                         // ---- the sink's owner augments along the path back to row `cur`.  Every log
@@ -740,7 +753,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = gtid + c * TC;
-            if (j >= P) continue;
+            if (j >= P || helper) continue;
             const int r = s.row4col[j];
 #ifndef MBX_PHASE_TIMING   // (timing builds use the mask buffer for the cycle counters)
             if (p.mask) p.mask[row0 + j] = r >= 0 ? 1 : 0;
@@ -877,10 +890,10 @@ struct KernelInfo {
     size_t occ_smem = 0;
 };
 
-template <int NWARPS, int C, int CL>
+template <int NWARPS, int C, int CL, int RSP = 1>
 int launch_one(const MatchParams &p, cudaStream_t st) {
     static thread_local KernelInfo info;
-    auto kern = mbx_match_loss_reg_kernel<NWARPS, C, CL>;
+    auto kern = mbx_match_loss_reg_kernel<NWARPS, C, CL, RSP>;
     const size_t smem = rcarve(nullptr, nullptr, p.P, p.M, NWARPS * CL, !(p.flags & MBX_FLAG_BOUNDARY));
     if (smem > static_cast<size_t>(max_smem_optin())) return MBX_E_TOO_LARGE;
     if (smem > info.configured_smem) {
@@ -935,6 +948,17 @@ int launch_one(const MatchParams &p, cudaStream_t st) {
 
 template <int NWARPS>
 int launch_cols(const MatchParams &p, int cols, int cl, cudaStream_t st) {
+    if (cl < 0) {   // row split: two warp groups that each hold every column (P <= 3 * 16 * NWARPS)
+        if constexpr (NWARPS == 8 || NWARPS == 16) {
+            switch (cols) {
+                case 1: return launch_one<NWARPS, 1, 1, 2>(p, st);
+                case 2: return launch_one<NWARPS, 2, 1, 2>(p, st);
+                case 3: return launch_one<NWARPS, 3, 1, 2>(p, st);
+                default: return MBX_E_TOO_LARGE;
+            }
+        }
+        return MBX_E_TOO_LARGE;
+    }
     if (cl > 1) {
         if constexpr (NWARPS == 8 || NWARPS == 16) {
             if (cl == 2 || (cl == 4 && NWARPS == 8)) {

@@ -186,6 +186,25 @@ def postprocess_heads(head_locations, head_confidences, bbox_priors, restriction
     return out
 
 
+def nms(boxes, scores, iou_threshold, max_keep=None, counts=None):
+    """Standalone batched greedy NMS on the GPU (extension; same kernel, `priors=None`):
+    boxes [B,n,4] f32 with coordinates in [0,1] (the detect path's normalised image coordinates --
+    the kernel clips to that range), scores [B,n] f32, optional counts [B] (valid boxes per row;
+    the rest is ignored).  Boxes are visited in descending score order (ties: higher index first)
+    and a box is dropped when an already kept one overlaps it with IoU > iou_threshold (strict,
+    fp32, torchvision's CPU arithmetic).  Only the top `max_keep` (default min(n, 1024)) by score
+    enter the suppression.  Returns (keep_idx i32 [B,k] padded with -1, count i32 [B])."""
+    b = _f32c(boxes, "boxes")
+    B, n = b.shape[0], b.shape[1]
+    s = _f32c(scores, "scores").view(B, n)
+    if counts is not None:
+        valid = torch.arange(n, device=b.device).view(1, n) < counts.view(B, 1)
+        s = torch.where(valid, s, torch.full_like(s, float("-inf")))
+    k = min(n, 1024) if max_keep is None else max(1, min(int(max_keep), 1024))
+    out = postprocess(b, s.view(B, n, 1), None, nms_iou=float(iou_threshold), k_max=k, want_patch_boxes=False)
+    return out["prior_idx"], out["count"]
+
+
 def detection_results(post, image_ids):
     """Host-side tail of the reference loop (detect.py:438-443): the list of
     {"image_id", "bbox", "score"} rows that detect.py dumps to JSON."""

@@ -189,3 +189,27 @@ def test_detect_step_host_path(cuda_device, use_graph):
             assert np.array_equal(out["prior_idx"][b, :c].numpy(), m["prior_idx"])
             assert np.array_equal(out["boxes"][b, :c].numpy(), m["boxes"])
             assert np.array_equal(out["scores"][b, :c].numpy(), m["scores"])
+
+
+def test_standalone_nms_vs_torchvision(cuda_device):
+    """detect.nms (the detect kernel with priors=None) against torchvision's CPU NMS and the oracle's
+    greedy loop: same kept indices in the same order.  Ragged counts via -inf padding."""
+    torchvision = pytest.importorskip("torchvision")
+    rng = np.random.default_rng(5)
+    B, n = 6, 300
+    ctr = rng.random((B, n, 2)).astype(np.float32) * 0.8 + 0.1
+    wh = rng.random((B, n, 2)).astype(np.float32) * 0.25 + 0.02
+    boxes = np.clip(np.concatenate([ctr - wh / 2, ctr + wh / 2], -1), 0, 1).astype(np.float32)
+    scores = rng.permutation(B * n).reshape(B, n).astype(np.float32) / np.float32(B * n)     # distinct
+    counts = np.array([300, 250, 1, 0, 300, 77], np.int32)
+    keep, cnt = detect.nms(dev(boxes), dev(scores), 0.4, counts=dev(counts))
+    torch.cuda.synchronize()
+    keep, cnt = keep.cpu().numpy(), cnt.cpu().numpy()
+    for b in range(B):
+        c = counts[b]
+        ref = torchvision.ops.nms(torch.from_numpy(boxes[b, :c]), torch.from_numpy(scores[b, :c]), 0.4).numpy()
+        order = np.argsort(scores[b, :c], kind="stable")[::-1]
+        ref2 = order[np_oracle.greedy_nms(boxes[b, :c][order], 0.4)] if c else np.zeros(0, np.int64)
+        assert np.array_equal(ref, ref2)
+        assert cnt[b] == len(ref) and np.array_equal(keep[b, :cnt[b]], ref), b
+        assert (keep[b, cnt[b]:] == -1).all()

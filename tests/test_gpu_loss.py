@@ -214,3 +214,31 @@ def test_step_object_host_mapped_results(cuda_device, use_graph):
     ll, cl = step.step_host(d["locations"], d["confidences"], d["gt"], d["num_gt"])      # and the object recovers
     ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], 1000.0)
     np.testing.assert_allclose([ll, cl], [ref["location_loss"], ref["confidence_loss"]], rtol=RTOL)
+
+
+@pytest.mark.parametrize("K,B,M,dist", [(5, 32, 20, "uniform"), (5, 12, 20, "full"), (5, 148, 100, "coco_person"), (5, 3, 200, "full")])
+def test_rowsplit_variant_is_bit_identical(cuda_device, K, B, M, dist):
+    """The row-split kernel variant (two warp groups share the batched first step by rows; default
+    when every image has an SM to itself) against the single-group variant: same bits everywhere,
+    and the same matches as the oracle."""
+    from multibox_b200 import _lib
+    d = synth.make_train_inputs(K=K, B=B, M=M, dist=dist, seed=300 + K, edge_cases=True)
+
+    def run(flags):
+        out = loss.match_loss_raw(dev(d["locations"]), dev(d["confidences"]).view(d["B"], d["P"]), dev(d["gt"]),
+                                  dev(d["num_gt"]), dev(d["priors"]), d["alpha"], flags=flags, want_mask=True,
+                                  want_gt_idx=True, want_stacked=True, want_grads=True)
+        torch.cuda.synchronize()
+        return {k: v.cpu().numpy() for k, v in out.items()}
+
+    a = run(_lib.FLAG_NO_ROWSPLIT)
+    b = run(_lib.FLAG_ROWSPLIT)
+    c = run(0)
+    assert a["results"][2] == 0 and b["results"][2] == 0
+    for o in (b, c):
+        for k in ("mask", "matched_gt_idx", "stacked_gt", "d_locations", "d_confidences"):
+            assert np.array_equal(a[k], o[k]), k
+        assert np.array_equal(a["results"][:8].view(np.uint32), o["results"][:8].view(np.uint32))
+    ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], d["alpha"])
+    assert np.array_equal(b["matched_gt_idx"], ref["matched_gt_idx"])
+    np.testing.assert_allclose(b["results"][:2], [ref["location_loss"], ref["confidence_loss"]], rtol=RTOL)
