@@ -129,20 +129,23 @@ __host__ __device__ inline size_t carve(Smem *s, unsigned char *base, int P, int
     return align_up(o, 16);
 }
 
-// Heavy-first processing order for the dynamically scheduled matching kernel: images sorted by
-// DESCENDING GT count (counting sort on 256 buckets; the order inside a bucket is arbitrary --
+// Heavy-first processing order for the dynamically scheduled matching kernel: the images beyond
+// the first wave (first..B-1) sorted by DESCENDING GT count (counting sort on 256 buckets; the order inside a bucket is arbitrary --
 // every consumer reads the same array, and the results do not depend on the processing order:
 // per-image partials are reduced in image order).  An image's solve time grows with its GT count,
 // so handing out the heavy images first bounds the tail of the launch by a LIGHT image's time
 // (longest-processing-time-first list scheduling).  One CTA of 1024 threads.
-__global__ void __launch_bounds__(1024) mbx_order_kernel(const int32_t *num_gt, const int32_t *gt_row, int B, int M,
-                                                         int32_t *order) {
+__global__ void __launch_bounds__(1024) mbx_order_kernel(const int32_t *num_gt, const int32_t *gt_row, int first,
+                                                         int B, int M, int32_t *order) {
     __shared__ int hist[256], start[256];
+    // let the dependent matching kernel start right away: its first wave does not need order[],
+    // and it executes griddepcontrol.wait (= this grid complete and flushed) before reading it
+    asm volatile("griddepcontrol.launch_dependents;");
     const int tid = threadIdx.x;
     const int shift = M < 256 ? 0 : (32 - __clz(M >> 8));   // bucket = n >> shift < 256
     if (tid < 256) hist[tid] = 0;
     __syncthreads();
-    for (int b = tid; b < B; b += 1024) {
+    for (int b = first + tid; b < B; b += 1024) {
         int n = image_num_gt(num_gt, gt_row, b);
         n = n < 0 ? 0 : (n > M ? M : n);
         atomicAdd(&hist[n >> shift], 1);
@@ -166,15 +169,16 @@ __global__ void __launch_bounds__(1024) mbx_order_kernel(const int32_t *num_gt, 
         }
     }
     __syncthreads();
-    for (int b = tid; b < B; b += 1024) {
+    for (int b = first + tid; b < B; b += 1024) {
         int n = image_num_gt(num_gt, gt_row, b);
         n = n < 0 ? 0 : (n > M ? M : n);
         order[atomicAdd(&start[n >> shift], 1)] = b;
     }
 }
 
-int launch_order(const int32_t *num_gt, const int32_t *gt_row, int B, int M, int32_t *order, cudaStream_t st) {
-    mbx_order_kernel<<<1, 1024, 0, st>>>(num_gt, gt_row, B, M, order);
+int launch_order(const int32_t *num_gt, const int32_t *gt_row, int first, int B, int M, int32_t *order,
+                 cudaStream_t st) {
+    mbx_order_kernel<<<1, 1024, 0, st>>>(num_gt, gt_row, first, B, M, order);
     return check_cuda(cudaGetLastError(), "launch mbx_order_kernel");
 }
 
@@ -519,6 +523,7 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_kernel(const Match
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    const unsigned st_pre = __ldcg(p.status), lseq_pre = __ldcg(p.queue + 1);
     double a = 0.0, c = 0.0;
     long long m = 0;
     for (int b = tid; b < p.B; b += T) {
@@ -543,7 +548,7 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_kernel(const Match
             C += s.red[NWARPS + w];
             Mt += s.pv[w];
         }
-        finalize_losses(p, A, C, Mt);
+        finalize_losses(p, A, C, Mt, st_pre, lseq_pre);
     }
 }
 

@@ -323,13 +323,23 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     if (is_poster && warp == 0) ar_post_pending(p);
 
     // Image scheduling.  Static (image = CTA index, stride = resident CTAs) when every image has
-    // its own CTA; otherwise DYNAMIC over the heavy-first order built by mbx_order_kernel: the
-    // first wave takes positions 0..n_work-1, later positions are claimed from a global counter.
-    // Thread 0 issues the claim when an image starts and reads it when the image is done, so the
-    // L2 round trip of the atomic is off the critical path.
+    // its own CTA; otherwise DYNAMIC: the first wave takes images 0..n_work-1 as they come, the
+    // remaining images are handed out from a global counter in the heavy-first order built by
+    // mbx_order_kernel (order[] covers images n_work..B-1).  Thread 0 issues the claim when an image
+    // starts and reads it when the image is done, so the L2 round trip of the atomic is off the
+    // critical path.  The order kernel is a PROGRAMMATIC dependency (griddepcontrol.wait right
+    // before order[] is first read): its launch + run time hides behind the first wave.
     const bool dyn = (CL == 1) && p.dynamic != 0;
+    bool order_ready = false;
     for (int q = is_poster ? p.B : static_cast<int>(blockIdx.x) / CL; q < p.B;) {
-        const int b = dyn ? p.order[q] : q;
+        int b = q;
+        if (dyn && q >= n_work) {
+            if (!order_ready) {
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                order_ready = true;
+            }
+            b = __ldcg(p.order + (q - n_work));
+        }
         unsigned claim = 0u;
         if (dyn && tid == 0) claim = atomicAdd(p.queue, 1u);
         const float4 *gg;
@@ -388,7 +398,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                     if (p.conf_out && !helper) p.conf_out[row0 + j] = cf[c];
                 }
                 const float ce = boundary ? cf[c] : __fadd_rn(cf[c], kEps32);   // loss.py:74
-                lc[c] = nplogf(ce);                                              // loss.py:21
+                lc[c] = n > 0 ? nplogf(ce) : 0.0f;   // loss.py:21 (only ever read for an image that has GT rows)
                 float w = __fsub_rn(1.0f, ce);                                   // loss.py:22-24
                 if (w > 1.0f) w = 1.0f;
                 if (w <= 0.0f) w = kEps32;
@@ -529,6 +539,39 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             double min_val = 0.0, ui = 0.0;
             unsigned scmask = invalid_mask;   // columns already scanned (or non-existent)
             unsigned dbl = 0u, updm = 0u;     // see spc64 / pm above
+            // The first Dijkstra step of this row is already known when its precomputed first-step
+            // minimum is unique and sits at a column whose dual is still zero: duals only raise
+            // reduced costs (v <= 0), so that column is the strict minimum of C(cur, j) - v[j] over
+            // all j, exactly what scanning row `cur` would select (the same argument as for the
+            // decisive rows above; the column is assigned, or the row would have been decisive).
+            // The scan, the block arg-min and the barrier of step 0 are skipped; the per-column
+            // first-step costs that step 0 would have left behind are formed at the start of step 1.
+            bool skip0 = false;
+            if constexpr (CL == 1) {
+                const uint2 rm0 = s.rowmin[cur];
+                const unsigned col0 = rm0.y & kColNone;
+                if (s.ctl[1] == 0 && !(rm0.y >> 31) && rm0.x < kOrdInf32 && col0 != kColNone && !s.dirty[col0]) {
+                    const int r4c0 = s.row4col[col0];
+                    if (r4c0 >= 0) {
+                        skip0 = true;
+                        min_val = static_cast<double>(unord32(rm0.x));
+                        const int cstar0 = static_cast<int>(col0) / TC;
+                        if (!helper && static_cast<int>(col0) - cstar0 * TC == gtid) {   // the column's owner logs the removal
+#pragma unroll
+                            for (int c = 0; c < C; ++c)
+                                if (c == cstar0) arow.set(c, static_cast<int>(col0), s.arow, static_cast<short>(r4c0));
+                            scmask |= 1u << cstar0;
+                            s.rm_col[0] = static_cast<int>(col0);
+                            s.rm_idx[0] = replay_pos(static_cast<int>(col0), 0, P, s.rm_idx);
+                            s.rm_pm[0] = 0;
+                            s.visit[1] = r4c0;
+                        }
+                        R = 1;
+                        i = r4c0;
+                        ui = s.u[i];
+                    }
+                }
+            }
             for (;;) {
                 const float4 g = s.gt[i];
                 unsigned long long key;
@@ -575,6 +618,20 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                     }
                     key = (bj == kPayNone) ? ~0ull : ord64(best);
                 } else {
+                    if (skip0 && R == 1) {   // what the skipped step 0 would have stored: C(cur, j) (- v[j] where v != 0)
+                        const float4 g0 = s.gt[cur];
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            if ((invalid_mask >> c) & 1u) continue;
+                            const int jc = gtid + c * TC;
+                            const float c32_0 = cost32(loc[c], g0, half_alpha, lc[c], l1[c]);
+                            c0.set(c, jc, s.c0, c32_0);
+                            if ((vnz >> c) & 1u) {
+                                spc.set(c, jc, s.spc, __dsub_rn(static_cast<double>(c32_0), cv.get(c, jc, s.cv)));
+                                dbl |= 1u << c;
+                            }
+                        }
+                    }
                     double best = INF;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
@@ -855,6 +912,8 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     block_sync<NWARPS>();
     if (!is_last) return;
     __threadfence();
+    // status word and previous launch sequence number: loaded together with the partials
+    const unsigned st_pre = __ldcg(p.status), lseq_pre = __ldcg(p.queue + 1);
     double a = 0.0, cc = 0.0, md = 0.0;
     for (int b = tid; b < p.B * CL; b += T) {
         a += __ldcg(p.partials + 2 * b);
@@ -878,7 +937,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             Cc += s.red[NWARPS + w];
             Mt += s.red[2 * NWARPS + w];
         }
-        finalize_losses(p, A, Cc, Mt);   // warp-cooperative (lane r posts to peer r)
+        finalize_losses(p, A, Cc, Mt, st_pre, lseq_pre);   // warp-cooperative (lane r posts to peer r)
     }
 }
 
@@ -936,10 +995,20 @@ int launch_one(const MatchParams &p, cudaStream_t st) {
     const bool poster = (CL == 1) && p.ar_world > 1 && (p.flags & MBX_FLAG_AR_DEFERRED);
     cfg.gridDim = dim3(units * CL + (poster ? 1 : 0));
     MatchParams pp = p;
+    cudaLaunchAttribute pdl[1];
     if (CL == 1 && p.B > units && !(p.flags & MBX_FLAG_STATIC)) {
-        // more images than resident CTAs: heavy-first order + dynamic scheduling
-        if (int e = launch_order(p.num_gt, p.gt_row, p.B, p.M, p.order, st)) return e;
+        // more images than resident CTAs: heavy-first order of the images beyond the first wave +
+        // dynamic scheduling; the matching kernel may start while the order kernel still runs
+        if (int e = launch_order(p.num_gt, p.gt_row, units, p.B, p.M, p.order, st)) return e;
         pp.dynamic = 1;
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cudaGetLastError();
+        if (cap == cudaStreamCaptureStatusNone) {   // (inside a graph capture the edge stays a full dependency)
+            pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            pdl[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = pdl;
+            cfg.numAttrs = 1;
+        }
     }
     return check_cuda(cudaLaunchKernelEx(&cfg, kern, pp), "launch mbx_match_loss_reg_kernel");
 }
