@@ -138,9 +138,6 @@ __host__ __device__ inline size_t carve(Smem *s, unsigned char *base, int P, int
 __global__ void __launch_bounds__(1024) mbx_order_kernel(const int32_t *num_gt, const int32_t *gt_row, int first,
                                                          int B, int M, int32_t *order) {
     __shared__ int hist[256], start[256];
-    // let the dependent matching kernel start right away: its first wave does not need order[],
-    // and it executes griddepcontrol.wait (= this grid complete and flushed) before reading it
-    asm volatile("griddepcontrol.launch_dependents;");
     const int tid = threadIdx.x;
     const int shift = M < 256 ? 0 : (32 - __clz(M >> 8));   // bucket = n >> shift < 256
     if (tid < 256) hist[tid] = 0;

@@ -323,23 +323,16 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     if (is_poster && warp == 0) ar_post_pending(p);
 
     // Image scheduling.  Static (image = CTA index, stride = resident CTAs) when every image has
-    // its own CTA; otherwise DYNAMIC: the first wave takes images 0..n_work-1 as they come, the
-    // remaining images are handed out from a global counter in the heavy-first order built by
-    // mbx_order_kernel (order[] covers images n_work..B-1).  Thread 0 issues the claim when an image
-    // starts and reads it when the image is done, so the L2 round trip of the atomic is off the
-    // critical path.  The order kernel is a PROGRAMMATIC dependency (griddepcontrol.wait right
-    // before order[] is first read): its launch + run time hides behind the first wave.
+    // its own CTA; otherwise DYNAMIC over the heavy-first order built by mbx_order_kernel: the
+    // first wave takes positions 0..n_work-1, later positions are claimed from a global counter.
+    // Thread 0 issues the claim when an image starts and reads it when the image is done, so the
+    // L2 round trip of the atomic is off the critical path.  (Making the order kernel a programmatic
+    // dependency -- first wave in index order, griddepcontrol.wait before order[] is first read --
+    // was measured: it hides the 4-5 us order kernel but gives up heavy-first for the first wave,
+    // which costs as much on skewed batches; not kept.)
     const bool dyn = (CL == 1) && p.dynamic != 0;
-    bool order_ready = false;
     for (int q = is_poster ? p.B : static_cast<int>(blockIdx.x) / CL; q < p.B;) {
-        int b = q;
-        if (dyn && q >= n_work) {
-            if (!order_ready) {
-                asm volatile("griddepcontrol.wait;" ::: "memory");
-                order_ready = true;
-            }
-            b = __ldcg(p.order + (q - n_work));
-        }
+        const int b = dyn ? __ldcg(p.order + q) : q;
         unsigned claim = 0u;
         if (dyn && tid == 0) claim = atomicAdd(p.queue, 1u);
         const float4 *gg;
@@ -995,20 +988,10 @@ int launch_one(const MatchParams &p, cudaStream_t st) {
     const bool poster = (CL == 1) && p.ar_world > 1 && (p.flags & MBX_FLAG_AR_DEFERRED);
     cfg.gridDim = dim3(units * CL + (poster ? 1 : 0));
     MatchParams pp = p;
-    cudaLaunchAttribute pdl[1];
     if (CL == 1 && p.B > units && !(p.flags & MBX_FLAG_STATIC)) {
-        // more images than resident CTAs: heavy-first order of the images beyond the first wave +
-        // dynamic scheduling; the matching kernel may start while the order kernel still runs
-        if (int e = launch_order(p.num_gt, p.gt_row, units, p.B, p.M, p.order, st)) return e;
+        // more images than resident CTAs: heavy-first order + dynamic scheduling
+        if (int e = launch_order(p.num_gt, p.gt_row, 0, p.B, p.M, p.order, st)) return e;
         pp.dynamic = 1;
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cudaGetLastError();
-        if (cap == cudaStreamCaptureStatusNone) {   // (inside a graph capture the edge stays a full dependency)
-            pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            pdl[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = pdl;
-            cfg.numAttrs = 1;
-        }
     }
     return check_cuda(cudaLaunchKernelEx(&cfg, kern, pp), "launch mbx_match_loss_reg_kernel");
 }
