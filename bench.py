@@ -330,6 +330,46 @@ def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True):
     return res
 
 
+def bench_layouts(d, barrier, steps=20, warmup=3):
+    """Per-head / ragged entry points against the reference's own layout steps done in torch."""
+    import torch
+    from multibox_b200 import loss, synth
+    B, P, M, K = d["B"], d["P"], d["M"], d["K"]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    hl, hc = synth.split_heads(d["locations"], d["logits"], K)
+    per_set = 4 * B * P * 5
+    nsets = max(2, min(64, (2 * L2_BYTES) // per_set + 1))
+    hls = [[torch.from_numpy(np.roll(t, r, axis=0).copy()).to(dev) for t in hl] for r in range(nsets)]
+    hcs = [[torch.from_numpy(np.roll(t, r, axis=0).copy()).to(dev) for t in hc] for r in range(nsets)]
+    gt = torch.from_numpy(d["gt"]).to(dev)
+    ng = torch.from_numpy(d["num_gt"]).to(dev)
+    flat, off = synth.ragged_gt(d["gt"], d["num_gt"])
+    flat_t, off_t = torch.from_numpy(flat).to(dev), torch.from_numpy(off).to(dev)
+    pri = torch.from_numpy(d["priors"]).to(dev)
+    out_dense = {}
+
+    def unfused(i):       # model.py:295-320 as torch ops, then the dense kernel (sigmoid fused either way)
+        loc, logit = loss.concat_heads(hls[i % nsets], hcs[i % nsets])
+        loss.match_loss_raw(loc.contiguous(), logit.view(B, P), gt, ng, pri, d["alpha"], flags=1, out=out_dense)
+
+    def fused(i):
+        loss.match_loss_heads_raw(hls[i % nsets], hcs[i % nsets], gt, ng, pri, d["alpha"], flags=1)
+
+    def fused_ragged(i):
+        loss.match_loss_heads_raw(hls[i % nsets], hcs[i % nsets], flat_t, None, pri, d["alpha"], flags=1,
+                                  gt_row_offsets=off_t, max_num_bboxes=M)
+
+    res = {"workload": "configs[3] shape (K=%d, P=%d, B=%d per GPU, M=%d): match + loss fwd/bwd from the six heads' "
+                       "NHWC outputs" % (K, P, B, M)}
+    for name, fn in (("concat_in_torch_then_dense_ms", unfused), ("fused_heads_ms", fused),
+                     ("fused_heads_ragged_gt_ms", fused_ragged)):
+        res[name] = 1e3 * time_region(fn, steps, warmup, barrier) / steps
+    res["note"] = ("the fused route never writes the concatenated [B,P,5] tensor nor splits its gradient "
+                   "(4 x 20P bytes per image of extra HBM traffic and 2+ extra launches in the un-fused route; "
+                   "the un-fused figure excludes the gradient split)")
+    return res
+
+
 def bench_detect(q, steps, warmup, barrier, nms_iou, want_e2e=True):
     import torch
     from multibox_b200 import detect
@@ -531,6 +571,10 @@ def main():
                          "note": "sparse GT: the step is dominated by the exact fp32 log / cost arithmetic "
                                  "(~58% issue-slot utilisation in ncu), not by HBM"},
         }
+        # ---- the data formats either side of the path, configs[3] shape:
+        # per-head NHWC inputs (concat + sigmoid fused away) and ragged ground truth, against the
+        # un-fused route (torch.cat of the six heads, then the dense entry point)
+        line["layouts"] = bench_layouts(d4, barrier)
         if rank == 0 and world == 1:
             line["cpu_baseline"] = cpu_baseline_train(d)
             line["cpu_baseline_c_port"] = cpu_baseline_train_c(d)

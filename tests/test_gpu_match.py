@@ -267,3 +267,15 @@ def test_large_batch_stress(cuda_device, warps, cluster):
         assert np.array_equal(m, m0)
         assert np.array_equal(gi, g0)
         assert np.array_equal(s, s0)
+
+
+def test_dynamic_schedule_wide_gt_range(cuda_device):
+    """MAX_NUM_BBOXES >= 256 (the order kernel buckets counts by n >> shift) with more images than
+    resident CTAs: every image against the C oracle."""
+    B, M = 700, 300
+    d = synth.make_train_inputs(K=5, B=B, M=M, dist="uniform", seed=123)
+    assert d["num_gt"].max() > 256
+    loc, conf = boundary_inputs(d)
+    m0, s0, g0 = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], B, d["alpha"])
+    m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], B, d["alpha"])
+    assert np.array_equal(m, m0) and np.array_equal(gi, g0) and np.array_equal(s, s0)
