@@ -352,12 +352,14 @@ def bench_layouts(d, barrier, steps=20, warmup=3):
         loc, logit = loss.concat_heads(hls[i % nsets], hcs[i % nsets])
         loss.match_loss_raw(loc.contiguous(), logit.view(B, P), gt, ng, pri, d["alpha"], flags=1, out=out_dense)
 
+    out_h, out_r = {}, {}
+
     def fused(i):
-        loss.match_loss_heads_raw(hls[i % nsets], hcs[i % nsets], gt, ng, pri, d["alpha"], flags=1)
+        loss.match_loss_heads_raw(hls[i % nsets], hcs[i % nsets], gt, ng, pri, d["alpha"], flags=1, out=out_h)
 
     def fused_ragged(i):
         loss.match_loss_heads_raw(hls[i % nsets], hcs[i % nsets], flat_t, None, pri, d["alpha"], flags=1,
-                                  gt_row_offsets=off_t, max_num_bboxes=M)
+                                  gt_row_offsets=off_t, max_num_bboxes=M, out=out_r)
 
     res = {"workload": "configs[3] shape (K=%d, P=%d, B=%d per GPU, M=%d): match + loss fwd/bwd from the six heads' "
                        "NHWC outputs" % (K, P, B, M)}

@@ -324,25 +324,36 @@ def make_heads_struct(head_locations, head_confidences, d_locations=None, d_conf
 
 def match_loss_heads_raw(head_locations, head_confidences, gt_bboxes, num_gt, priors, alpha, flags=0,
                          gt_row_offsets=None, max_num_bboxes=None, want_mask=False, want_gt_idx=False,
-                         want_grads=True, want_conf_out=False):
+                         want_grads=True, want_conf_out=False, out=None):
     """``mbx_match_loss_heads``: the training step fed from the per-head conv outputs.  Returns a dict
-    with per-head gradient lists ``d_head_locations`` / ``d_head_confidences`` (same shapes as the inputs)."""
+    with per-head gradient lists ``d_head_locations`` / ``d_head_confidences`` (same shapes as the
+    inputs).  `out` (a dict returned by an earlier call with the same shapes) re-uses the outputs."""
     lib = _lib.load()
     hl = [_f32c(t, "head_locations") for t in head_locations]
     hc = [_f32c(t, "head_confidences") for t in head_confidences]
     dev = hl[0].device
-    dl = [torch.empty_like(t) for t in hl] if want_grads else None
-    dc = [torch.empty_like(t) for t in hc] if want_grads else None
+    out = {} if out is None else out
+    dl = dc = None
+    if want_grads:
+        dl = out.get("d_head_locations") or [torch.empty_like(t) for t in hl]
+        dc = out.get("d_head_confidences") or [torch.empty_like(t) for t in hc]
     hs, B, P = make_heads_struct(hl, hc, dl, dc)
     if P != priors.shape[0]:
         raise ValueError("heads hold %d priors, bbox_priors %d" % (P, priors.shape[0]))
     M = int(max_num_bboxes) if gt_row_offsets is not None else gt_bboxes.shape[1]
-    out = {"d_head_locations": dl, "d_head_confidences": dc}
-    mask = torch.empty((B * P,), dtype=torch.int32, device=dev) if want_mask else None
-    gt_idx = torch.empty((B * P,), dtype=torch.int32, device=dev) if want_gt_idx else None
-    conf_out = torch.empty((B, P, 1), dtype=torch.float32, device=dev) if want_conf_out else None
-    results = torch.empty((_lib.RESULT_WORDS,), dtype=torch.float32, device=dev)
-    out.update(mask=mask, matched_gt_idx=gt_idx, confidences=conf_out, results=results)
+
+    def buf(name, want, shape, dtype):
+        if not want:
+            return None
+        t = out.get(name)
+        return t if t is not None else torch.empty(shape, dtype=dtype, device=dev)
+
+    mask = buf("mask", want_mask, (B * P,), torch.int32)
+    gt_idx = buf("matched_gt_idx", want_gt_idx, (B * P,), torch.int32)
+    conf_out = buf("confidences", want_conf_out, (B, P, 1), torch.float32)
+    results = buf("results", True, (_lib.RESULT_WORDS,), torch.float32)
+    out.update(d_head_locations=dl, d_head_confidences=dc, mask=mask, matched_gt_idx=gt_idx, confidences=conf_out,
+               results=results)
     ws = _workspace(dev, lib.mbx_match_workspace_bytes(B, P, M))
     rc = lib.mbx_match_loss_heads(ctypes.byref(hs), _lib.ptr(gt_bboxes), _lib.ptr(num_gt), _lib.ptr(gt_row_offsets),
                                   _lib.ptr(priors), B, P, M, float(alpha), int(flags),
