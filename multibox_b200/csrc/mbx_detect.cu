@@ -478,7 +478,17 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const unsigned di = __shfl_sync(0xffffffffu, d, i);   // whom box i suppresses (bits > i)
-                        if (!(removed & (1u << i))) removed |= di;
+                        // removed |= (bit i of removed clear) ? di : 0 -- as test-to-predicate + predicated OR:
+                        // two dependent instructions per step on the 32-step chain instead of three
+                        asm("{\n"
+                            ".reg .pred p;\n"
+                            ".reg .b32 t;\n"
+                            "and.b32 t, %0, %2;\n"
+                            "setp.eq.u32 p, t, 0;\n"
+                            "@p or.b32 %0, %0, %1;\n"
+                            "}\n"
+                            : "+r"(removed)
+                            : "r"(di), "r"(1u << i));
                     }
                     const unsigned kept = ~removed;
                     if (lane == c) keptw = kept;
@@ -553,8 +563,11 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
                         }
                     }
                 };
-                if (nwords >= 3)
+                // boxes per lane: the split that leaves the fewest empty (chunk, lane) slots
+                if (nwords >= 7 || nwords == 4)
                     cross(std::integral_constant<int, 4>{});
+                else if (nwords >= 3)       // 6 = 3+3, 5 = 3+2, 3
+                    cross(std::integral_constant<int, 3>{});
                 else if (nwords == 2)
                     cross(std::integral_constant<int, 2>{});
                 else

@@ -213,3 +213,25 @@ def test_standalone_nms_vs_torchvision(cuda_device):
         assert np.array_equal(ref, ref2)
         assert cnt[b] == len(ref) and np.array_equal(keep[b, :cnt[b]], ref), b
         assert (keep[b, cnt[b]:] == -1).all()
+
+
+@pytest.mark.parametrize("warps", [0, 4, 16])
+def test_detect_nms_many_chunks(cuda_device, warps):
+    """max_to_keep = 1024 (32 chunks of 32 survivors: more later chunks than warps), clustered boxes so
+    that whole chunks are suppressed, and plain random boxes."""
+    d = synth.make_detect_inputs(K=11, B=6, keep=1024, seed=31)
+    rng = np.random.default_rng(32)
+    centres = rng.random((6, 12, 4)).astype(np.float32)
+    for b in range(3):      # images 0-2: every prior snaps to one of 12 cluster boxes (+ jitter)
+        c = centres[b][rng.integers(0, 12, d["P"])]
+        x1, x2 = np.minimum(c[:, 0], c[:, 2]) * 0.8, np.maximum(c[:, 0], c[:, 2]) * 0.8 + 0.1
+        y1, y2 = np.minimum(c[:, 1], c[:, 3]) * 0.8, np.maximum(c[:, 1], c[:, 3]) * 0.8 + 0.1
+        box = np.stack([x1, y1, x2, y2], 1) + rng.normal(0, 0.004, (d["P"], 4)).astype(np.float32)
+        d["locations"][b] = box.astype(np.float32) - d["priors"]
+    for thr in (0.5, 0.8):
+        post = np_oracle.postprocess(d["locations"], d["confidences"], d["priors"], d["restrictions"],
+                                     d["max_to_keep"], d["offsets"], d["patch_dims"], d["image_dims"],
+                                     d["is_flipped"], nms_iou=thr)
+        counts = [m["boxes"].shape[0] for m in post]
+        assert min(counts) < 200 and max(counts) > 600
+        _compare(_run(d, nms_iou=thr, k_max=1024, warps=warps), post)
