@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_kernel(const Match
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    const unsigned st_pre = __ldcg(p.status), lseq_pre = __ldcg(p.queue + 1);
+    const TailPrefetch pre = tail_prefetch(p);
     double a = 0.0, c = 0.0;
     long long m = 0;
     for (int b = tid; b < p.B; b += T) {
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_kernel(const Match
             C += s.red[NWARPS + w];
             Mt += s.pv[w];
         }
-        finalize_losses(p, A, C, Mt, st_pre, lseq_pre);
+        finalize_losses(p, A, C, Mt, pre);
     }
 }
 

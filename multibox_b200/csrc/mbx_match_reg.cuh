@@ -906,7 +906,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     if (!is_last) return;
     __threadfence();
     // status word and previous launch sequence number: loaded together with the partials
-    const unsigned st_pre = __ldcg(p.status), lseq_pre = __ldcg(p.queue + 1);
+    const TailPrefetch pre = tail_prefetch(p);
     double a = 0.0, cc = 0.0, md = 0.0;
     for (int b = tid; b < p.B * CL; b += T) {
         a += __ldcg(p.partials + 2 * b);
@@ -930,7 +930,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             Cc += s.red[NWARPS + w];
             Mt += s.red[2 * NWARPS + w];
         }
-        finalize_losses(p, A, Cc, Mt, st_pre, lseq_pre);   // warp-cooperative (lane r posts to peer r)
+        finalize_losses(p, A, Cc, Mt, pre);   // warp-cooperative (lane r posts to peer r)
     }
 }
 
