@@ -285,6 +285,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     const double INF = CUDART_INF;
     unsigned status = 0;
 
+    if constexpr (CL > 1) cg::this_cluster().sync();   // every CTA of the cluster runs before any remote shared-memory access
     __shared__ HeadTab sh_heads[MBX_MAX_HEADS];
     const int nheads = p.nheads;
     if (nheads > 1) stage_heads(p, sh_heads);
@@ -633,7 +634,10 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                         const double r =
                             __dsub_rn(__dsub_rn(__dadd_rn(min_val, static_cast<double>(c32)), ui), cv.get(c, jc, s.cv));
                         const bool live = !((scmask >> c) & 1u);
-                        const double old = ((dbl >> c) & 1u) ? spc.get(c, jc, s.spc) : static_cast<double>(c0.get(c, jc, s.c0));
+                        // (a column that is not live -- scanned or non-existent -- never reads column state:
+                        // the in-bounds dummy index of a non-existent column belongs to another thread)
+                        double old = INF;
+                        if (live) old = ((dbl >> c) & 1u) ? spc.get(c, jc, s.spc) : static_cast<double>(c0.get(c, jc, s.c0));
                         const bool upd = live && (r < old);
                         if (upd) {
                             spc.set(c, jc, s.spc, r);
