@@ -115,3 +115,21 @@ for w in ([warps] if warps else [8]):
         tot = t[sel].mean(0).mean(0)
         print("cfg4-shape warps=%d: %d images with n=%d, mean cycles by phase: %s  total %.0f" %
               (w, len(sel), want, " ".join("%s=%.0f" % (nm.split()[0], tot[k]) for k, nm in enumerate(names)), tot.sum()))
+
+# configs[4]-shaped images (K=11, P=1420, M=200, n ~ U{0..200}): where the solver's time goes
+d = synth.make_train_inputs(K=11, B=148, M=200, dist="uniform", seed=1005)
+B, P = d["B"], d["P"]
+for w in ([warps] if warps in (8, 16) else [16]):
+    out = {"mask": torch.zeros(max(B * P, B * 16 * 10 * 2 * 4 + 64), dtype=torch.int32, device="cuda")}
+    for _ in range(2):
+        loss.match_loss_raw(dev(d["locations"]), dev(d["confidences"]).view(B, P), dev(d["gt"]), dev(d["num_gt"]),
+                            dev(d["priors"]), d["alpha"], want_mask=True, warps=w, out=out)
+    torch.cuda.synchronize()
+    t = out["mask"].cpu().numpy().view(np.int64)[:B * w * 10].reshape(B, w, 10)[:, :, :8]
+    for lo, hi in ((0, 20), (40, 60), (90, 110), (140, 160), (180, 200)):
+        sel = np.where((d["num_gt"] >= lo) & (d["num_gt"] <= hi))[0]
+        if len(sel) == 0:
+            continue
+        tot = t[sel].mean(0).mean(0)
+        print("cfg5-shape warps=%d: %d images with n in [%d,%d], mean cycles by phase: %s  total %.0f" %
+              (w, len(sel), lo, hi, " ".join("%s=%.0f" % (nm.split()[0], tot[k]) for k, nm in enumerate(names)), tot.sum()))
