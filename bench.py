@@ -304,7 +304,7 @@ def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True):
         hsteps = []
         for r in range(hsets):
             hs = loss.MultiboxLossStep(B, P, M, d["priors"], d["alpha"], device=dev, use_graph=True, peer=peer,
-                                       deferred_allreduce=True, host_results=True)
+                                       deferred_allreduce=True, host_results=True, zero_copy=True)
             np.copyto(hs.h_loc.numpy(), np.roll(d["locations"], r, axis=0))
             np.copyto(hs.h_conf.numpy(), np.roll(d["confidences"].reshape(B, P), r, axis=0))
             np.copyto(hs.h_gt.numpy(), np.roll(d["gt"], r, axis=0))
@@ -493,10 +493,15 @@ def main():
                                                     "finds its inputs in L2" % tr["nsets"]),
         "e2e": {"value": world * B * args.steps / e2e_sec, "unit": "images/s",
                 "h2d_bytes_per_step": tr["h2d"], "d2h_bytes_per_step": tr["d2h"],
-                "how": "MultiboxLossStep.step_pinned(use_graph=True, host_results=True): one CUDA-graph launch = 1 "
-                       "packed pinned H2D copy + 1 kernel (with the loss all-reduce fused in when N > 1) that stores "
-                       "the 64-byte loss/status block straight into mapped pinned host memory; the host polls the "
-                       "launch sequence word and checks the status, every step; wall clock"},
+                "how": "MultiboxLossStep.step_pinned(use_graph=True, host_results=True, zero_copy=True): the step's "
+                       "inputs sit in one packed PINNED host buffer; one CUDA-graph launch = 1 kernel that streams "
+                       "them over PCIe itself (read-once 16-byte loads from the mapped buffer: the host->device "
+                       "transfer happens inside the kernel, h2d_bytes_per_step bytes every step), solves, and "
+                       "stores the 64-byte loss/status block straight into mapped pinned host memory (with the loss "
+                       "all-reduce fused in when N > 1); the host polls the launch sequence word and checks the "
+                       "status, every step; gradients stay on the device for the backward pass; wall clock.  "
+                       "Measured alternatives (profiles/e2e_modes.py): H2D copy node + D2H copy + stream sync "
+                       "45.7 us, H2D copy node + polled host results 35.3 us, this mode 32.4 us per step"},
         "gpu_launches": tr["launches_per_step"] * args.steps,
         "collective": ("loss SUM all-reduce fused into the kernel (NVLink peer stores + system-scope arrival "
                        "counters, 4-deep slot ring); step k posts its sums and completes step k-1's reduction, the "

@@ -419,7 +419,7 @@ class MultiboxLossStep:
 
     def __init__(self, B, P, M, priors, alpha, device="cuda", logits=False, want_mask=False,
                  want_stacked=False, warps=0, use_graph=False, peer=None, deferred_allreduce=False,
-                 host_results=False):
+                 host_results=False, zero_copy=False):
         self.B, self.P, self.M, self.alpha = B, P, M, float(alpha)
         self.device = torch.device(device)
         if self.device.index is None:
@@ -454,6 +454,10 @@ class MultiboxLossStep:
         # memory and the host polls the launch sequence word (results[15]) -- no D2H copy node, no
         # stream synchronisation on the step's critical path.  Host-buffer path only.
         self.host_results = bool(host_results)
+        # zero_copy: the kernel reads the packed inputs straight from the MAPPED PINNED staging buffer
+        # over PCIe (its streaming, read-once 16-byte loads are the host->device transfer): no H2D
+        # copy node in front of the kernel.  Host-buffer path only.
+        self.zero_copy = bool(zero_copy)
         if self.host_results:
             self.flags |= _lib.FLAG_HOST_RESULTS
             self.out["results"] = self.h_res
@@ -473,13 +477,18 @@ class MultiboxLossStep:
                               want_gt_idx=self.want_mask, want_stacked=self.want_stacked,
                               want_grads=True, warps=self.warps, out=self.out, peer=self.peer)
 
-    def prepare(self, locations, confidences, gt, num_gt):
+    def prepare(self, locations, confidences, gt, num_gt, inputs=None):
         """Returns a zero-argument callable that launches the step on these (fixed)
         device tensors with all ctypes arguments pre-marshalled: the launch costs a
-        single foreign call (for latency-critical loops and CUDA-graph capture)."""
+        single foreign call (for latency-critical loops and CUDA-graph capture).
+        `inputs` (four tensors) replaces the input POINTERS of the closure after the outputs were
+        set up with the device tensors -- used for mapped pinned host inputs (zero_copy)."""
         import ctypes as c
         lib = _lib.load()
         out = self.step(locations, confidences, gt, num_gt)     # allocates outputs / workspace once
+        if inputs is not None:
+            torch.cuda.current_stream(self.device).synchronize()
+            locations, confidences, gt, num_gt = inputs
         B, P, M = self.B, self.P, self.M
         ws = _workspace(self.device, lib.mbx_match_workspace_bytes(B, P, M))
         flags = int(self.flags) | (int(self.warps) << _lib.FLAG_WARPS_SHIFT)
@@ -506,8 +515,9 @@ class MultiboxLossStep:
         return launch
 
     def _enqueue_host_step(self):
-        self.d_in.copy_(self.h_in, non_blocking=True)           # one H2D copy of the packed inputs
-        self._launch()                                           # one kernel
+        if not self.zero_copy:
+            self.d_in.copy_(self.h_in, non_blocking=True)       # one H2D copy of the packed inputs
+        self._launch()                                           # one kernel (zero_copy: reads h_in itself)
         if not self.host_results:
             self.h_res.copy_(self.out["results"], non_blocking=True)  # losses + status (64 bytes)
 
@@ -527,7 +537,8 @@ class MultiboxLossStep:
 
     def _ensure_ready(self):
         if self._launch is None:
-            self._launch = self.prepare(self.d_loc_in, self.d_conf_in, self.d_gt_in, self.d_ng_in)
+            host = (self.h_loc, self.h_conf, self.h_gt, self.h_ng) if self.zero_copy else None
+            self._launch = self.prepare(self.d_loc_in, self.d_conf_in, self.d_gt_in, self.d_ng_in, inputs=host)
             torch.cuda.current_stream(self.device).synchronize()
         if self.use_graph and self._graph is None:
             side = torch.cuda.Stream(device=self.device)

@@ -187,13 +187,13 @@ def test_dynamic_schedule_matches_static(cuda_device):
     assert np.array_equal(dy["matched_gt_idx"].reshape(-1)[:64 * P], ref["matched_gt_idx"])
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_step_object_host_mapped_results(cuda_device, use_graph):
+@pytest.mark.parametrize("use_graph,zero_copy", [(False, False), (True, False), (True, True), (False, True)])
+def test_step_object_host_mapped_results(cuda_device, use_graph, zero_copy):
     """host_results=True: the kernel stores the result block into mapped pinned host memory and the
     host polls the launch sequence word instead of synchronising -- same numbers, step after step."""
     B = 32
     step = loss.MultiboxLossStep(B, 646, 20, synth.make_train_inputs(K=5, B=1, M=20, seed=0)["priors"], 1000.0,
-                                 use_graph=use_graph, host_results=True)
+                                 use_graph=use_graph, host_results=True, zero_copy=zero_copy)
     plain = loss.MultiboxLossStep(B, 646, 20, step.priors, 1000.0, use_graph=False)
     for seed in (1002, 7, 8, 9, 10):
         d = synth.make_train_inputs(K=5, B=B, M=20, seed=seed)
