@@ -372,7 +372,7 @@ def bench_layouts(d, barrier, steps=20, warmup=3):
     return res
 
 
-def bench_detect(q, steps, warmup, barrier, nms_iou, want_e2e=True):
+def bench_detect(q, steps, warmup, barrier, nms_iou, want_e2e=True, zero_copy=False):
     import torch
     from multibox_b200 import detect
     B, P, keep = q["B"], q["P"], q["keep"]
@@ -407,7 +407,8 @@ def bench_detect(q, steps, warmup, barrier, nms_iou, want_e2e=True):
         hsets = 2
         dsteps_ = []
         for r in range(hsets):
-            ds = detect.DetectStep(B, P, keep, q["priors"], nms_iou=nms_iou, device=dev, use_graph=True)
+            ds = detect.DetectStep(B, P, keep, q["priors"], nms_iou=nms_iou, device=dev, use_graph=True,
+                                   zero_copy=zero_copy)
             ds.fill_host(**{k: np.roll(q[k], r, axis=0) for k in names})
             dsteps_.append(ds)
 

@@ -38,3 +38,25 @@ for name, kw in modes:
         torch.cuda.synchronize()
         res.append((time.perf_counter() - t0) / 300 * 1e6)
     print("%-52s %6.1f us per step (min of 3: %.1f)  losses %s" % (name, np.median(res), min(res), v))
+
+
+# detect (configs[2]): packed host inputs -> packed host outputs
+from multibox_b200 import detect  # noqa: E402
+q = synth.make_detect_inputs(**synth.DETECT_CONFIGS["cfg3"])
+names = ("locations", "confidences", "restrictions", "max_to_keep", "offsets", "patch_dims", "image_dims", "is_flipped")
+for name, kw in (("detect: H2D copy + kernel + D2H copy (graph)", dict(zero_copy=False)),
+                 ("detect: zero-copy (kernel reads / writes the pinned buffers)", dict(zero_copy=True))):
+    steps = []
+    for r in range(2):
+        ds = detect.DetectStep(q["B"], q["P"], q["keep"], q["priors"], nms_iou=0.5, use_graph=True, **kw)
+        ds.fill_host(**{k: np.roll(q[k], r, axis=0) for k in names})
+        steps.append(ds)
+    for i in range(10):
+        steps[i % 2].run_pinned()
+    res = []
+    for rep in range(3):
+        t0 = time.perf_counter()
+        for i in range(100):
+            out = steps[i % 2].run_pinned()
+        res.append((time.perf_counter() - t0) / 100 * 1e6)
+    print("%-62s %6.1f us per step (min %.1f)  count[0]=%d" % (name, np.median(res), min(res), int(out["count"][0])))

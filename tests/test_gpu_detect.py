@@ -172,12 +172,12 @@ def test_full_size_properties(cuda_device):
     assert np.array_equal(out["prior_idx"], out2["prior_idx"])
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_detect_step_host_path(cuda_device, use_graph):
+@pytest.mark.parametrize("use_graph,zero_copy", [(False, False), (True, False), (True, True), (False, True)])
+def test_detect_step_host_path(cuda_device, use_graph, zero_copy):
     d = synth.make_detect_inputs(K=5, B=9, keep=60, seed=21, patches=True)      # odd B: section alignment
     names = ("locations", "confidences", "restrictions", "max_to_keep", "offsets", "patch_dims", "image_dims",
              "is_flipped")
-    step = detect.DetectStep(9, d["P"], 60, d["priors"], nms_iou=0.5, use_graph=use_graph)
+    step = detect.DetectStep(9, d["P"], 60, d["priors"], nms_iou=0.5, use_graph=use_graph, zero_copy=zero_copy)
     post = np_oracle.postprocess(d["locations"], d["confidences"], d["priors"], d["restrictions"],
                                  d["max_to_keep"], d["offsets"], d["patch_dims"], d["image_dims"],
                                  d["is_flipped"], nms_iou=0.5)
