@@ -1,8 +1,6 @@
 """Builds a -DMBX_PHASE_TIMING copy of the library into gpurun_out/ and prints the per-phase cycle
 totals of the register-resident matching kernel (GPU box).  python profiles/phase_timing.py [warps]"""
-import ctypes
 import os
-import subprocess
 import sys
 
 import numpy as np
