@@ -243,3 +243,38 @@ def test_eval_topk_shape():
     assert len(rows) == 200 and len(rows[0]) == 7 and rows[0][6] == 1
     sc = [r[5] for r in rows[:100]]
     assert all(sc[i] >= sc[i + 1] for i in range(99))
+
+
+def test_loss_graph_vs_torch_autograd():
+    """Independent check of the oracle's restatement of the TF graph part (loss.py:67-74,88-101) and
+    of the hand-derived gradients: the same statements written with torch CPU
+    ops -- index_select for tf.dynamic_partition, the four sentinel rows of loss.py:94-97 kept,
+    sum(t**2)/2 for tf.nn.l2_loss -- and differentiated by autograd, as TF's autodiff would."""
+    import torch
+    d = synth.make_train_inputs(K=5, B=5, M=20, seed=77, edge_cases=True)
+    ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], d["alpha"])
+    B, P = d["B"], d["P"]
+    loc_in = torch.from_numpy(d["locations"]).requires_grad_(True)
+    conf_in = torch.from_numpy(d["confidences"]).requires_grad_(True)
+    priors = torch.from_numpy(d["priors"])
+    locations = loc_in.reshape(-1, 4) + priors.repeat(B, 1)                      # loss.py:67,70-71
+    confidences = conf_in.reshape(-1) + np.float32(np_oracle.SMALL_EPSILON)      # loss.py:68,74
+    matching = torch.from_numpy(ref["mask"].astype(np.int64))                    # the py_func's outputs are constants
+    stacked = torch.from_numpy(ref["stacked_gt"])
+    i0, i1 = torch.nonzero(matching == 0).flatten(), torch.nonzero(matching == 1).flatten()
+    unmatched_locations, matched_locations = locations.index_select(0, i0), locations.index_select(0, i1)   # :88
+    unmatched_confidences, matched_confidences = confidences.index_select(0, i0), confidences.index_select(0, i1)
+    matched_locations = torch.cat([matched_locations, torch.zeros(1, 4)], 0)     # :94-97
+    stacked = torch.cat([stacked, torch.zeros(1, 4)], 0)
+    matched_confidences = torch.cat([matched_confidences, torch.ones(1)], 0)
+    unmatched_confidences = torch.cat([unmatched_confidences, torch.zeros(1)], 0)
+    diff = matched_locations - stacked
+    location_loss = d["alpha"] * (diff.double() ** 2).sum() / 2.                 # :100 (fp64 sum: order-free)
+    confidence_loss = -1. * torch.log(matched_confidences).double().sum() \
+        - torch.log((1. - unmatched_confidences) + np.float32(np_oracle.SMALL_EPSILON)).double().sum()   # :101
+    assert unmatched_locations.shape[0] == B * P - int(ref["mask"].sum())
+    (location_loss + confidence_loss).backward()
+    np.testing.assert_allclose(location_loss.item(), ref["location_loss_f64"], rtol=1e-7)
+    np.testing.assert_allclose(confidence_loss.item(), ref["confidence_loss_f64"], rtol=1e-6)
+    np.testing.assert_allclose(loc_in.grad.numpy(), ref["d_locations"], rtol=1e-5, atol=0)
+    np.testing.assert_allclose(conf_in.grad.numpy(), ref["d_confidences"], rtol=1e-5, atol=0)
