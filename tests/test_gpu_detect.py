@@ -235,3 +235,25 @@ def test_detect_nms_many_chunks(cuda_device, warps):
         counts = [m["boxes"].shape[0] for m in post]
         assert min(counts) < 200 and max(counts) > 600
         _compare(_run(d, nms_iou=thr, k_max=1024, warps=warps), post)
+
+
+@pytest.mark.parametrize("P,keep,B", [(5, 200, 3), (33, 64, 1), (130, 200, 7), (257, 1024, 2)])
+def test_detect_small_prior_sets(cuda_device, P, keep, B):
+    """Prior sets smaller than max_to_keep / than one sort tile, single-image batches: every valid
+    prior survives the top-k, NMS and conversion still match the oracle."""
+    rng = np.random.default_rng(P)
+    pri = rng.random((P, 4)).astype(np.float32) * 0.5
+    pri[:, 2:] = pri[:, :2] + 0.05 + rng.random((P, 2)).astype(np.float32) * 0.4
+    d = dict(priors=pri, locations=rng.normal(0, 0.02, (B, P, 4)).astype(np.float32),
+             confidences=rng.random((B, P, 1)).astype(np.float32),
+             restrictions=np.tile(np.array([0, 0, 1, 1], np.float32), (B, 1)),
+             max_to_keep=np.full((B, 1), keep, np.int32), offsets=np.zeros((B, 2), np.int32),
+             patch_dims=np.full((B, 2), 300, np.int32), image_dims=np.full((B, 2), 300, np.int32),
+             is_flipped=np.zeros((B, 1), np.int32))
+    for nms in (None, 0.3):
+        post = np_oracle.postprocess(d["locations"], d["confidences"], d["priors"], d["restrictions"],
+                                     d["max_to_keep"], d["offsets"], d["patch_dims"], d["image_dims"],
+                                     d["is_flipped"], nms_iou=nms)
+        if nms is None:
+            assert all(m["boxes"].shape[0] == min(P, keep) for m in post)
+        _compare(_run(d, nms_iou=nms, k_max=keep), post)

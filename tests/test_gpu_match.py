@@ -279,3 +279,15 @@ def test_dynamic_schedule_wide_gt_range(cuda_device):
     m0, s0, g0 = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], B, d["alpha"])
     m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], B, d["alpha"])
     assert np.array_equal(m, m0) and np.array_equal(gi, g0) and np.array_equal(s, s0)
+
+
+def test_single_image_and_tiny_batches(cuda_device):
+    """B = 1, 2, 3 (fewer images than any scheduling granularity), with and without GT."""
+    for B in (1, 2, 3):
+        d = synth.make_train_inputs(K=5, B=B, M=20, dist="full" if B != 2 else "uniform", seed=50 + B)
+        if B == 1:
+            d["num_gt"][:] = 0
+        loc, conf = boundary_inputs(d)
+        m0, s0, g0 = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], B, d["alpha"])
+        m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], B, d["alpha"])
+        assert np.array_equal(m, m0) and np.array_equal(gi, g0) and np.array_equal(s.reshape(-1, 4), s0.reshape(-1, 4))
