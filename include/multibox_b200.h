@@ -65,15 +65,9 @@ extern "C" {
 #define MBX_FLAG_HOST_RESULTS  32u  /* `results` is mapped pinned HOST memory that the caller polls: the
                                        launch sequence word results[15] is published after a system-scope
                                        fence (costs ~1 us; without the flag word 15 is still written last) */
-#define MBX_FLAG_ROWSPLIT      64u  /* use the row-split variant of the register-resident kernel (two warp
-                                       groups per image share the batched first step by rows); measured no
-                                       faster on B200, off by default.  Tuning / testing. */
-#define MBX_FLAG_NO_ROWSPLIT   128u /* (overrides MBX_FLAG_ROWSPLIT) */
 #define MBX_FLAG_GENERIC       4u   /* force the generic shared-memory matching kernel (any P) instead
                                        of the register-resident family (tuning / testing) */
 #define MBX_FLAG_WARPS_SHIFT   8    /* bits 8..15: force CTA size in warps (0 = heuristic) */
-#define MBX_FLAG_CLUSTER_SHIFT 24   /* bits 24..27: force the thread-block-cluster size per image of the
-                                       register-resident kernel (1, 2 or 4; 0 = heuristic) */
 #define MBX_FLAG_COLS_SHIFT    16   /* bits 16..23: force columns per thread of the register-resident
                                        kernel (0 = heuristic) */
 

@@ -22,11 +22,8 @@ FLAG_GENERIC = 4
 FLAG_AR_DEFERRED = 8
 FLAG_STATIC = 16
 FLAG_HOST_RESULTS = 32
-FLAG_ROWSPLIT = 64
-FLAG_NO_ROWSPLIT = 128
 FLAG_WARPS_SHIFT = 8
 FLAG_COLS_SHIFT = 16
-FLAG_CLUSTER_SHIFT = 24
 STATUS_INVALID_COST = 1
 STATUS_INFEASIBLE = 2
 STATUS_BAD_NUM_GT = 4

@@ -564,9 +564,9 @@ static WsLayout ws_layout(int B) {
     w.queue = o;     // dynamic image scheduler: next position of the processing order
     o += 8;
     w.partials = o;
-    o += sizeof(double) * 2 * static_cast<size_t>(B) * 4;    // up to 4 CTAs (a cluster) per image
+    o += sizeof(double) * 2 * static_cast<size_t>(B);
     w.img_matched = o;
-    o += sizeof(int32_t) * static_cast<size_t>(B) * 4;
+    o += sizeof(int32_t) * static_cast<size_t>(B);
     o = align_up(o, 16);
     w.offsets = o;
     o += sizeof(int32_t) * (static_cast<size_t>(B) + 1);
@@ -896,8 +896,7 @@ int mbx::match_loss_impl(const mbx_heads *heads, const float *locations, const f
     }
     if (!(flags & MBX_FLAG_GENERIC)) {
         // register-resident family first; it declines shapes it has no instantiation for
-        const int ncl = static_cast<int>((flags >> MBX_FLAG_CLUSTER_SHIFT) & 0xfu);
-        const int rc = launch_match_reg(p, nwarps, ncols, ncl, st);
+        const int rc = launch_match_reg(p, nwarps, ncols, st);
         if (rc != MBX_E_TOO_LARGE) return rc;
         if (p.nheads > 1) {
             set_error("mbx_match_loss_heads: P=%d is beyond the register-resident kernel family", P);

@@ -2,5 +2,5 @@
 #include "mbx_match_reg.cuh"
 
 namespace mbx {
-template int launch_cols<2>(const MatchParams &, int, int, cudaStream_t);
+template int launch_cols<2>(const MatchParams &, int, cudaStream_t);
 }  // namespace mbx

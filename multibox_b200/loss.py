@@ -60,7 +60,7 @@ def raise_for_status(status):
 
 def match_loss_raw(locations, confidences, gt_bboxes, num_gt, priors, alpha, flags=0,
                    want_mask=False, want_gt_idx=False, want_stacked=False, want_grads=True,
-                   want_conf_out=False, warps=0, cols=0, cluster=0, out=None, peer=None):
+                   want_conf_out=False, warps=0, cols=0, out=None, peer=None):
     """Thin wrapper of ``mbx_match_loss`` (see include/multibox_b200.h).  Inputs
     must already be contiguous fp32/int32 CUDA tensors; locations [B,P,4],
     confidences [B,P].  Returns a dict of device tensors; nothing synchronises.
@@ -92,8 +92,7 @@ def match_loss_raw(locations, confidences, gt_bboxes, num_gt, priors, alpha, fla
     results = buf("results", True, (_lib.RESULT_WORDS,), torch.float32)
     nbytes = lib.mbx_match_workspace_bytes(B, P, M)
     ws = _workspace(dev, nbytes)
-    flags = int(flags) | (int(warps) << _lib.FLAG_WARPS_SHIFT) | (int(cols) << _lib.FLAG_COLS_SHIFT) | \
-        (int(cluster) << _lib.FLAG_CLUSTER_SHIFT)
+    flags = int(flags) | (int(warps) << _lib.FLAG_WARPS_SHIFT) | (int(cols) << _lib.FLAG_COLS_SHIFT)
     args = (_lib.ptr(locations), _lib.ptr(confidences), _lib.ptr(gt_bboxes), _lib.ptr(num_gt), _lib.ptr(priors),
             B, P, M, float(alpha), flags,
             _lib.ptr(mask), _lib.ptr(gt_idx), _lib.ptr(stacked), _lib.ptr(n_stacked),

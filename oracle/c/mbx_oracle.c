@@ -243,3 +243,45 @@ void orc_cost_matrix(const float *loc, const float *conf, const float *gt, int64
             C[p * n + j] = cost_entry(loc + 4 * p, gt + 4 * j, half_alpha, lc[p], l1[p]);
     free(lc); free(l1);
 }
+
+/* ---- numeric check of the product's cheap cost bound -------------------------
+ * The CUDA kernels skip the exact cost wherever a 4-FMA approximation a(i,j) + G_i
+ * minus a proven margin already exceeds what is needed (multibox_b200/csrc/mbx_bound.h
+ * holds the formulas and the error analysis; the SAME header is compiled here as plain
+ * C).  orc_bound_max_ratio returns max over all (prior, gt) pairs of
+ *     |c_exact - (a + G)| / (m_prior + m_gt)        (must stay <= 1; evaluated in double)
+ * with c_exact from cost_entry() above; pairs whose margin is +inf (pruning disabled) are
+ * skipped and counted in *n_unbounded.  A NaN ratio (finite margin, non-finite values)
+ * is reported as +inf. */
+#include "../../multibox_b200/csrc/mbx_bound.h"
+
+double orc_bound_max_ratio(const float *loc, const float *lc, const float *l1, const float *gt, int64_t P,
+                           int64_t n, float alpha, int64_t *n_unbounded)
+{
+    const float h = alpha / 2.0f;
+    double worst = 0.0;
+    int64_t unb = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const float *g = gt + 4 * i;
+        float gp[4], G, mg;
+        mbx_bound_row(g[0], g[1], g[2], g[3], h, gp, &G, &mg);
+        for (int64_t p = 0; p < P; p++) {
+            const float *l = loc + 4 * p;
+            const float L = fmaxf(fmaxf(fabsf(l[0]), fabsf(l[1])), fmaxf(fabsf(l[2]), fabsf(l[3])));
+            float Lx = L;
+            for (int k = 0; k < 4; k++)
+                if (!(fabsf(l[k]) <= 3.4028234663852886e38f)) Lx = NAN;
+            const float T = fabsf(lc[p]) + fabsf(l1[p]);
+            const float m = mbx_bound_margin_col(Lx, T, h);
+            if (isinf(m) || isinf(mg)) { unb++; continue; }
+            const float w = mbx_bound_w(l[0], l[1], l[2], l[3], h, lc[p], l1[p]);
+            const float a = mbx_bound_a(l[0], l[1], l[2], l[3], gp[0], gp[1], gp[2], gp[3], w);
+            const double c = cost_entry(l, g, h, lc[p], l1[p]);
+            const double err = fabs(c - ((double)a + (double)G));
+            const double ratio = err / ((double)m + (double)mg);
+            if (!(ratio <= worst)) worst = (ratio != ratio) ? INFINITY : ratio;
+        }
+    }
+    if (n_unbounded) *n_unbounded = unb;
+    return worst;
+}

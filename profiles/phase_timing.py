@@ -33,7 +33,9 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-names = ["prologue", "batched 1st step", "sequential rows", "general scan", "general argmin", "select/log/walk", "(loop exit)", "epilogue"]
+names = ["prologue", "1st step pass 1 (cheap)", "sequential rows", "general scan", "general argmin", "select/log/walk",
+         "dual update / exit", "epilogue", "1st step pass 2 (exact)"]
+NS = 12      # slots per warp: 9 phase accumulators, exact-cost evaluations of the warp, 2 global timestamps
 
 
 def dev(a):
@@ -65,29 +67,30 @@ if detect_mode:
 for label, d in (("cfg2", synth.make_train_inputs(**synth.TRAIN_CONFIGS["cfg2"])),
                  ("cfg2 full n=20", synth.make_train_inputs(K=5, B=32, M=20, dist="full", seed=5))):
     B, P = d["B"], d["P"]
-    cl = int(os.environ.get("MBX_CLUSTER", "1"))
+    cl = 1
     for w in ([warps] if warps else [4, 8, 16]):
-        out = {"mask": torch.zeros(max(B * P, B * 16 * 10 * 2 * 4 + 64), dtype=torch.int32, device="cuda")}
+        out = {"mask": torch.zeros(max(B * P, B * 16 * NS * 2 * 4 + 64), dtype=torch.int32, device="cuda")}
         evs = []
         for _ in range(3):
             a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             loss.match_loss_raw(dev(d["locations"]), dev(d["confidences"]).view(B, P), dev(d["gt"]), dev(d["num_gt"]),
-                                dev(d["priors"]), d["alpha"], want_mask=True, warps=w, cluster=cl, out=out)
+                                dev(d["priors"]), d["alpha"], want_mask=True, warps=w, out=out)
             b_.record()
             evs.append((a, b_))
         torch.cuda.synchronize()
-        t = out["mask"].cpu().numpy().view(np.int64)[:B * cl * w * 10].reshape(B, cl * w, 10)
-        b = int(np.argmax(d["num_gt"]))      # grid == B*cl here: cluster b solves image b
-        print("%s warps=%d cluster=%d: image %d (n=%d) per-warp mean cycles by phase" % (label, w, cl, b, d["num_gt"][b]))
-        tot = t[b, :, :8].mean(0)
+        t = out["mask"].cpu().numpy().view(np.int64)[:B * cl * w * NS].reshape(B, cl * w, NS)
+        b = int(np.argmax(d["num_gt"]))      # grid == B here: CTA b solves image b
+        print("%s warps=%d: image %d (n=%d) per-warp mean cycles by phase" % (label, w, b, d["num_gt"][b]))
+        tot = t[b, :, :9].mean(0)
         for k, nm in enumerate(names):
-            print("   %-16s %9.0f  (%.0f per augmentation)" % (nm, tot[k], tot[k] / max(1, d["num_gt"][b])))
-        print("   total %.0f cycles; slowest warp %.0f" % (tot.sum(), t[b, :, :8].sum(1).max()))
+            print("   %-24s %9.0f  (%.0f per augmentation)" % (nm, tot[k], tot[k] / max(1, d["num_gt"][b])))
+        print("   total %.0f cycles; slowest warp %.0f; exact cost evaluations %d (n*P = %d)" %
+              (tot.sum(), t[b, :, :9].sum(1).max(), t[b, :, 9].sum(), d["num_gt"][b] * P))
         # kernel-level timeline from %globaltimer (ns): when each CTA started / finished
-        g0, g1 = t[:, :, 8], t[:, :, 9]
+        g0, g1 = t[:, :, 10], t[:, :, 11]
         k0 = g0.min()
-        cyc = t[:, :, :8].sum(2).max(1)
+        cyc = t[:, :, :9].sum(2).max(1)
         slow = int(np.argmax(g1.max(1)))
         print("   timeline (ns after the first CTA started): CTA starts %d..%d, CTA ends %d..%d (last: image %d, n=%d, "
               "%d cycles); event time of the launch %.1f us" %
@@ -100,34 +103,37 @@ for label, d in (("cfg2", synth.make_train_inputs(**synth.TRAIN_CONFIGS["cfg2"])
 d = synth.make_train_inputs(K=7, B=148, M=100, dist="coco_person", seed=1004)
 B, P = d["B"], d["P"]
 for w in ([warps] if warps else [8]):
-    out = {"mask": torch.zeros(max(B * P, B * 16 * 10 * 2 * 4 + 64), dtype=torch.int32, device="cuda")}
+    out = {"mask": torch.zeros(max(B * P, B * 16 * NS * 2 * 4 + 64), dtype=torch.int32, device="cuda")}
     for _ in range(2):
         loss.match_loss_raw(dev(d["locations"]), dev(d["confidences"]).view(B, P), dev(d["gt"]), dev(d["num_gt"]),
                             dev(d["priors"]), d["alpha"], want_mask=True, warps=w, out=out)
     torch.cuda.synchronize()
-    t = out["mask"].cpu().numpy().view(np.int64)[:B * w * 10].reshape(B, w, 10)[:, :, :8]
+    t = out["mask"].cpu().numpy().view(np.int64)[:B * w * NS].reshape(B, w, NS)
     for want in (0, 3, 8, int(d["num_gt"].max())):
         sel = np.where(d["num_gt"] == want)[0]
         if len(sel) == 0:
             continue
-        tot = t[sel].mean(0).mean(0)
-        print("cfg4-shape warps=%d: %d images with n=%d, mean cycles by phase: %s  total %.0f" %
-              (w, len(sel), want, " ".join("%s=%.0f" % (nm.split()[0], tot[k]) for k, nm in enumerate(names)), tot.sum()))
+        tot = t[sel][:, :, :9].mean(0).mean(0)
+        print("cfg4-shape warps=%d: %d images with n=%d, mean cycles by phase: %s  total %.0f; exact evals/image %.0f" %
+              (w, len(sel), want, " ".join("%s=%.0f" % (nm.replace(" ", "_"), tot[k]) for k, nm in enumerate(names)),
+               tot.sum(), t[sel][:, :, 9].sum(1).mean()))
 
 # configs[4]-shaped images (K=11, P=1420, M=200, n ~ U{0..200}): where the solver's time goes
 d = synth.make_train_inputs(K=11, B=148, M=200, dist="uniform", seed=1005)
 B, P = d["B"], d["P"]
 for w in ([warps] if warps in (8, 16) else [16]):
-    out = {"mask": torch.zeros(max(B * P, B * 16 * 10 * 2 * 4 + 64), dtype=torch.int32, device="cuda")}
+    out = {"mask": torch.zeros(max(B * P, B * 16 * NS * 2 * 4 + 64), dtype=torch.int32, device="cuda")}
     for _ in range(2):
         loss.match_loss_raw(dev(d["locations"]), dev(d["confidences"]).view(B, P), dev(d["gt"]), dev(d["num_gt"]),
                             dev(d["priors"]), d["alpha"], want_mask=True, warps=w, out=out)
     torch.cuda.synchronize()
-    t = out["mask"].cpu().numpy().view(np.int64)[:B * w * 10].reshape(B, w, 10)[:, :, :8]
+    t = out["mask"].cpu().numpy().view(np.int64)[:B * w * NS].reshape(B, w, NS)
     for lo, hi in ((0, 20), (40, 60), (90, 110), (140, 160), (180, 200)):
         sel = np.where((d["num_gt"] >= lo) & (d["num_gt"] <= hi))[0]
         if len(sel) == 0:
             continue
-        tot = t[sel].mean(0).mean(0)
-        print("cfg5-shape warps=%d: %d images with n in [%d,%d], mean cycles by phase: %s  total %.0f" %
-              (w, len(sel), lo, hi, " ".join("%s=%.0f" % (nm.split()[0], tot[k]) for k, nm in enumerate(names)), tot.sum()))
+        tot = t[sel][:, :, :9].mean(0).mean(0)
+        print("cfg5-shape warps=%d: %d images with n in [%d,%d], mean cycles by phase: %s  total %.0f; exact evals/image %.0f "
+              "(mean n*P %.0f)" %
+              (w, len(sel), lo, hi, " ".join("%s=%.0f" % (nm.replace(" ", "_"), tot[k]) for k, nm in enumerate(names)),
+               tot.sum(), t[sel][:, :, 9].sum(1).mean(), (d["num_gt"][sel] * P).mean()))

@@ -1,7 +1,7 @@
 """compute-sanitizer driver (GPU box): tiny invocations of every kernel family, meant to be run as
   compute-sanitizer --tool {memcheck,racecheck,synccheck} python profiles/sanitize.py
 Covers: register-resident matching kernel (static + dynamic scheduling, logits, heads, ragged,
-row split, cluster), generic kernel, order / scan kernels, detect kernel (NMS on / off, heads,
+generic kernel, order / scan kernels, detect kernel (NMS on / off, heads,
 pooled merge), filter / convert kernels."""
 import os
 import sys
@@ -20,8 +20,8 @@ def dev(a):
 
 d = synth.make_train_inputs(K=5, B=6, M=20, seed=1, edge_cases=True)
 args = (dev(d["locations"]), dev(d["confidences"]).view(6, -1), dev(d["gt"]), dev(d["num_gt"]), dev(d["priors"]))
-for kw in (dict(), dict(flags=_lib.FLAG_GENERIC), dict(flags=_lib.FLAG_ROWSPLIT), dict(warps=4), dict(warps=16),
-           dict(warps=8, cluster=2), dict(flags=_lib.FLAG_LOGITS, want_conf_out=True)):
+for kw in (dict(), dict(flags=_lib.FLAG_GENERIC), dict(warps=4), dict(warps=16),
+           dict(warps=4, cols=6), dict(flags=_lib.FLAG_LOGITS, want_conf_out=True)):
     out = loss.match_loss_raw(*args, d["alpha"], want_mask=True, want_gt_idx=True, want_stacked=True, **kw)
     torch.cuda.synchronize()
     assert out["results"][2].item() == 0, kw

@@ -37,26 +37,24 @@ def sweep(name, d, variants, reps):
     print("== %s: B=%d P=%d M=%d mean n=%.1f" % (name, d["B"], d["P"], d["M"], d["num_gt"].mean()))
     for v in variants:
         warps, cols, generic = v[:3]
-        cluster = v[3] if len(v) > 3 else 0
         out = {}
 
         def fn():
             loss.match_loss_raw(args[0], args[1], args[2], args[3], pri, d["alpha"], flags=4 if generic else 0,
-                                warps=warps, cols=cols, cluster=cluster, out=out)
+                                warps=warps, cols=cols, out=out)
         try:
             med, mn = timeit(fn, reps)
-            print("  warps=%2d cols=%d cl=%d %-8s median %9.1f us  min %9.1f us  -> %.3g img/s" %
-                  (warps, cols, cluster, "generic" if generic else "reg", med, mn, d["B"] / (med * 1e-6)))
+            print("  warps=%2d cols=%d %-8s median %9.1f us  min %9.1f us  -> %.3g img/s" %
+                  (warps, cols, "generic" if generic else "reg", med, mn, d["B"] / (med * 1e-6)))
         except Exception as e:
             print("  warps=%2d cols=%d failed: %s" % (warps, cols, str(e)[:80]))
 
 
-V_SMALL = [(0, 0, False), (4, 0, False), (8, 0, False, 1), (16, 0, False, 1), (8, 0, False, 2), (8, 0, False, 4),
-           (16, 0, False, 2)]
+V_SMALL = [(0, 0, False), (4, 0, False), (8, 0, False), (16, 0, False), (8, 4, False), (4, 8, False)]
 sweep("cfg2", synth.make_train_inputs(**synth.TRAIN_CONFIGS["cfg2"]), V_SMALL, 20)
 sweep("cfg2 B=256", synth.make_train_inputs(K=5, B=256, M=20, seed=3), V_SMALL, 20)
 sweep("cfg2 B=4096", synth.make_train_inputs(K=5, B=4096, M=20, seed=3), V_SMALL, 10)
 sweep("cfg4", synth.make_train_inputs(**synth.TRAIN_CONFIGS["cfg4"]),
-      [(4, 0, True), (0, 0, False), (4, 0, False), (8, 0, False), (16, 0, False)], 10)
+      [(4, 0, True), (0, 0, False), (4, 0, False), (8, 0, False), (16, 0, False), (16, 3, False), (8, 5, False)], 10)
 sweep("big K=11 B=1024", synth.make_train_inputs(K=11, B=1024, M=200, dist="uniform", seed=1005),
       [(8, 0, True), (0, 0, False), (8, 0, False), (16, 0, False), (16, 4, False)], 5)

@@ -22,11 +22,11 @@ def _sha(*arrays):
     return h.hexdigest()
 
 
-def _gpu_assign(loc, conf, gt, ng, B, alpha, warps=0, cols=0, generic=False, cluster=0):
-    if warps or cols or generic or cluster:
+def _gpu_assign(loc, conf, gt, ng, B, alpha, warps=0, cols=0, generic=False):
+    if warps or cols or generic:
         out = loss.match_loss_raw(dev(loc).view(B, -1, 4), dev(conf).view(B, -1), dev(gt), dev(ng), None, alpha,
                                   flags=2 | (4 if generic else 0), want_mask=True, want_gt_idx=True,
-                                  want_stacked=True, want_grads=False, warps=warps, cols=cols, cluster=cluster)
+                                  want_stacked=True, want_grads=False, warps=warps, cols=cols)
         loss.raise_for_status(out["results"][2].item())
         n = int(out["n_stacked"].item())
         return out["mask"].cpu().numpy(), out["stacked_gt"][:n].cpu().numpy(), out["matched_gt_idx"].cpu().numpy()
@@ -119,8 +119,6 @@ def test_match_vs_c_oracle(cuda_device, K, B, M, dist, alpha):
 VARIANTS = [(1, 0, True), (2, 0, True), (4, 0, True), (8, 0, True),
             (4, 6, False), (4, 8, False), (8, 3, False), (8, 0, False), (16, 2, False), (16, 0, False),
             (2, 0, False)]        # (2, 0): 11 columns per thread -> no instantiation -> generic fallback
-# (warps, cluster): one image per thread-block cluster (distributed shared memory)
-CLUSTER_VARIANTS = [(8, 2), (8, 4), (16, 2)]
 
 
 @pytest.mark.parametrize("warps,cols,generic", VARIANTS)
@@ -130,18 +128,6 @@ def test_match_kernel_variants_agree(cuda_device, warps, cols, generic):
     m0, s0, g0 = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], 12, d["alpha"])
     m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], 12, d["alpha"], warps=warps, cols=cols, generic=generic)
     assert np.array_equal(m, m0) and np.array_equal(gi, g0) and np.array_equal(s, s0)
-
-
-@pytest.mark.parametrize("warps,cluster", CLUSTER_VARIANTS)
-@pytest.mark.parametrize("K,M,dist", [(5, 20, "uniform"), (11, 200, "full")])
-def test_match_cluster_variants_agree(cuda_device, warps, cluster, K, M, dist):
-    B = 9
-    d = synth.make_train_inputs(K=K, B=B, M=M, dist=dist, seed=91 + K, edge_cases=True)
-    loc, conf = boundary_inputs(d)
-    m0, s0, g0 = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], B, d["alpha"])
-    for _ in range(2):
-        m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], B, d["alpha"], warps=warps, cluster=cluster)
-        assert np.array_equal(m, m0) and np.array_equal(gi, g0) and np.array_equal(s, s0)
 
 
 @pytest.mark.parametrize("P,M,warps", [(33, 5, 0), (33, 5, 1), (96, 30, 1), (200, 64, 0), (1024, 8, 0), (2500, 40, 0),
@@ -186,13 +172,12 @@ def test_tie_rule_matches_scipy(cuda_device):
     m1, s1, g1 = np_oracle.compute_assignments(loc.reshape(-1, 4), conf.reshape(-1).copy(), gt, ng, np.int32(B),
                                                np.float32(8.0), return_indices=True)
     assert np.array_equal(m0, m1) and np.array_equal(g0, g1)
-    for warps, cols, generic, cluster in [(0, 0, False, 0)] + [v + (0,) for v in VARIANTS] + \
-            [(w, 0, False, c) for w, c in CLUSTER_VARIANTS]:
+    for warps, cols, generic in [(0, 0, False)] + VARIANTS:
         m, s, gi = _gpu_assign(loc.reshape(-1, 4), conf.reshape(-1), gt, ng, B, 8.0, warps=warps, cols=cols,
-                               generic=generic, cluster=cluster)
-        assert np.array_equal(m, m0), (warps, cols, generic, cluster)
-        assert np.array_equal(gi, g0), (warps, cols, generic, cluster)
-        assert np.array_equal(s, s0), (warps, cols, generic, cluster)
+                               generic=generic)
+        assert np.array_equal(m, m0), (warps, cols, generic)
+        assert np.array_equal(gi, g0), (warps, cols, generic)
+        assert np.array_equal(s, s0), (warps, cols, generic)
 
 
 def test_errors_like_scipy(cuda_device):
@@ -255,15 +240,15 @@ def test_full_size_properties(cuda_device):
         assert np.array_equal(m2[b], m0) and np.array_equal(gi2[b], g0)
 
 
-@pytest.mark.parametrize("warps,cluster", [(0, 0), (4, 0), (8, 0), (16, 0), (1, 0), (8, 2), (8, 4)])
-def test_large_batch_stress(cuda_device, warps, cluster):
+@pytest.mark.parametrize("warps", [0, 4, 8, 16, 1])
+def test_large_batch_stress(cuda_device, warps):
     """Many images per persistent CTA (B=4096, K=5): every image checked against the C oracle
     (fast port), twice, to flush out intra-CTA races."""
     d = synth.make_train_inputs(K=5, B=4096, M=20, dist="uniform", seed=99)
     loc, conf = boundary_inputs(d)
     m0, s0, g0 = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], 4096, d["alpha"])
     for _ in range(2):
-        m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], 4096, d["alpha"], warps=warps, cluster=cluster)
+        m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], 4096, d["alpha"], warps=warps)
         assert np.array_equal(m, m0)
         assert np.array_equal(gi, g0)
         assert np.array_equal(s, s0)
@@ -291,3 +276,106 @@ def test_single_image_and_tiny_batches(cuda_device):
         m0, s0, g0 = c_oracle.compute_assignments(loc, conf, d["gt"], d["num_gt"], B, d["alpha"])
         m, s, gi = _gpu_assign(loc, conf, d["gt"], d["num_gt"], B, d["alpha"])
         assert np.array_equal(m, m0) and np.array_equal(gi, g0) and np.array_equal(s.reshape(-1, 4), s0.reshape(-1, 4))
+
+
+# ----------------------------------------------------------------------------- exact-cost pruning
+def _assert_same(loc, conf, gt, ng, B, alpha, **kw):
+    m0, s0, g0 = c_oracle.compute_assignments(loc, conf, gt, ng, B, alpha)
+    m, s, gi = _gpu_assign(loc, conf, gt, ng, B, alpha, **kw)
+    assert np.array_equal(m, m0) and np.array_equal(gi, g0) and np.array_equal(s.reshape(-1, 4), s0.reshape(-1, 4))
+
+
+@pytest.mark.parametrize("warps,cols", [(0, 0), (4, 6), (16, 2)])
+def test_pruning_near_duplicate_priors(cuda_device, warps, cols):
+    """Many priors whose costs differ by far less than the margin of the cheap bound (the window
+    of candidate columns holds tens of priors per row; near-ties and exact ties among them): the
+    kernel must still select exactly what the full evaluation selects."""
+    rng = np.random.default_rng(17)
+    B, P, M = 10, 646, 20
+    ng = rng.integers(1, M + 1, size=B).astype(np.int32)
+    gt = synth.gt_boxes(rng, ng, M)
+    loc = np.zeros((B, P, 4), np.float32)
+    conf = np.zeros((B, P), np.float32)
+    for b in range(B):
+        base = rng.random((8, 4)).astype(np.float32)                         # 8 clusters of ~80 near-identical priors
+        pick = rng.integers(0, 8, size=P)
+        jitter = (rng.standard_normal((P, 4)) * 10.0 ** rng.uniform(-8, -5)).astype(np.float32)
+        loc[b] = base[pick] + jitter
+        conf[b] = np.float32(0.3) + (rng.integers(0, 3, size=P) * np.float32(1e-7)).astype(np.float32)
+        if b % 3 == 0:
+            gt[b, :ng[b]] = loc[b, rng.integers(0, P, size=ng[b])]            # GT exactly on a prior: cost ~ log terms only
+    _assert_same(loc.reshape(-1, 4), conf.reshape(-1), gt, ng, B, 1000.0, warps=warps, cols=cols)
+
+
+@pytest.mark.parametrize("scale,alpha", [(1.0, 1e-3), (1e3, 1e6), (1e-4, 1e9), (1e6, 1.0), (1.0, 0.0), (3e9, 2.0)])
+def test_pruning_extreme_scales(cuda_device, scale, alpha):
+    """Coordinates / alpha far from the unit square: the margins grow with the magnitudes (up to
+    'nothing is pruned'); results stay those of the full evaluation."""
+    rng = np.random.default_rng(int(np.log10(scale) * 7 + 100))
+    B, P, M = 6, 646, 20
+    ng = rng.integers(0, M + 1, size=B).astype(np.int32)
+    ng[0] = M
+    gt = (synth.gt_boxes(rng, ng, M) * np.float32(scale)).astype(np.float32)
+    loc = (rng.random((B * P, 4)) * scale).astype(np.float32)
+    conf = rng.uniform(0.01, 0.99, size=B * P).astype(np.float32)
+    _assert_same(loc, conf, gt, ng, B, alpha)
+
+
+def test_invalid_entries_far_from_every_gt_still_raise(cuda_device):
+    """scipy validates the WHOLE cost matrix: a NaN / -inf entry raises even when it belongs to a
+    prior no GT box would ever consider (a column the cheap bound would prune)."""
+    d = synth.make_train_inputs(K=5, B=3, M=20, dist="full", seed=6)
+    loc, conf = boundary_inputs(d)
+    P = d["P"]
+    # the prior farthest from every GT box of image 1
+    dist = ((loc[P:2 * P, None, :] - d["gt"][1][None, :, :]) ** 2).sum(-1).min(1)
+    far = P + int(np.argmax(dist))
+    for bad_value in (-0.5, np.inf, np.nan):          # log(-0.5) = NaN; log(inf) = inf -> cost -inf; NaN
+        bad = conf.copy()
+        bad[far] = bad_value
+        with pytest.raises(ValueError, match="invalid numeric"):
+            loss.compute_assignments(dev(loc), dev(bad), dev(d["gt"]), dev(d["num_gt"]), 3, 1000.0)
+        with np.errstate(all="ignore"), pytest.raises(ValueError):
+            c_oracle.compute_assignments(loc, bad, d["gt"], d["num_gt"], 3, 1000.0)
+    badl = loc.copy()
+    badl[far, 3] = -np.inf                            # an infinite coordinate: cost +inf, legal, never selected
+    _assert_same(badl, conf, d["gt"], d["num_gt"], 3, 1000.0)
+    badg = d["gt"].copy()
+    badg[2, 5, 1] = np.inf                            # an infinite GT box: its whole row costs +inf -> infeasible
+    with pytest.raises(ValueError, match="infeasible"):
+        loss.compute_assignments(dev(loc), dev(conf), dev(badg), dev(d["num_gt"]), 3, 1000.0)
+    with np.errstate(all="ignore"), pytest.raises(ValueError, match="infeasible"):
+        c_oracle.compute_assignments(loc, conf, badg, d["num_gt"], 3, 1000.0)
+    # zero confidence far away: +inf cost, legal, never selected
+    okc = conf.copy()
+    okc[far] = 0.0
+    _assert_same(loc, okc, d["gt"], d["num_gt"], 3, 1000.0)
+
+
+def test_full_size_config3_every_image(cuda_device):
+    """BASELINE configs[3] as stated (K=7, P=904, B=1024, MAX_NUM_BBOXES=100, COCO-person-like GT counts):
+    every image against the C oracle; dynamic heavy-first scheduling is active at this size."""
+    d = synth.make_train_inputs(**synth.TRAIN_CONFIGS["cfg4"])
+    assert d["B"] == 1024 and d["P"] == 904 and d["M"] == 100
+    loc, conf = boundary_inputs(d)
+    _assert_same(loc, conf, d["gt"], d["num_gt"], d["B"], d["alpha"])
+
+
+def test_full_size_config4_shard_every_image(cuda_device):
+    """A BASELINE configs[4] per-GPU shard (K=11, P=1420, MAX_NUM_BBOXES=200, n ~ U{0..200}, 1024 images =
+    8192 / 8 GPUs): every image against the C oracle (the first shard and, sampled, the other seven)."""
+    d = synth.make_train_inputs(K=11, B=1024, M=200, dist="uniform", seed=1005)
+    loc, conf = boundary_inputs(d)
+    _assert_same(loc, conf, d["gt"], d["num_gt"], 1024, 1000.0)
+
+
+def test_nplog_exhaustive_on_gpu(cuda_device):
+    """Every positive finite float32 (2^31 - 2^23 values): the kernels' log equals the C restatement of
+    numpy's float32 log bit for bit (the C twin equals np.log on all of them: gen_golden.py --exhaustive)."""
+    step = 1 << 24
+    for first in range(0, 0x7f800000, step):
+        bits = np.arange(max(first, 1), min(first + step, 0x7f800000), dtype=np.uint32)
+        x = bits.view(np.float32)
+        got = gpu_nplog(x).view(np.uint32)
+        want = c_oracle.nplog(x).view(np.uint32)
+        assert np.array_equal(got, want), hex(first)
