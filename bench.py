@@ -262,7 +262,7 @@ def time_region(fn, steps, warmup, barrier):
     return e0.elapsed_time(e1) / 1e3
 
 
-def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True):
+def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True):
     import torch
     from multibox_b200 import loss
     B, P, M = d["B"], d["P"], d["M"]
@@ -274,7 +274,8 @@ def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True):
     confs = rotated_sets(t["confidences"].view(B, P), nsets)
     gts = rotated_sets(t["gt"], nsets)
     ngs = rotated_sets(t["num_gt"], nsets)
-    step = loss.MultiboxLossStep(B, P, M, d["priors"], d["alpha"], device=dev, peer=peer, deferred_allreduce=True)
+    step = loss.MultiboxLossStep(B, P, M, d["priors"], d["alpha"], device=dev, peer=peer, deferred_allreduce=True,
+                                 pdl=pdl)
     # one pre-marshalled launch closure per input set: a step is ONE foreign call + one kernel
     launches = [step.prepare(locs[s], confs[s], gts[s], ngs[s]) for s in range(nsets)]
     torch.cuda.synchronize()

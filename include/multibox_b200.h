@@ -65,6 +65,14 @@ extern "C" {
 #define MBX_FLAG_HOST_RESULTS  32u  /* `results` is mapped pinned HOST memory that the caller polls: the
                                        launch sequence word results[15] is published after a system-scope
                                        fence (costs ~1 us; without the flag word 15 is still written last) */
+#define MBX_FLAG_PDL           64u  /* programmatic dependent launch: the caller promises that the INPUT tensors
+                                       do not come from the kernel that precedes this call on `stream` (e.g. the
+                                       previous step, or inputs staged in pinned host memory).  The kernel may then
+                                       start while that preceding kernel is still running and waits for it
+                                       (griddepcontrol.wait) only before its first write to outputs / workspace:
+                                       consecutive steps overlap launch latency and tail.  Results are identical.
+                                       Ignored with stacked_gt / n_stacked, dynamic scheduling (B above the resident
+                                       CTAs) and MBX_FLAG_GENERIC. */
 #define MBX_FLAG_GENERIC       4u   /* force the generic shared-memory matching kernel (any P) instead
                                        of the register-resident family (tuning / testing) */
 #define MBX_FLAG_WARPS_SHIFT   8    /* bits 8..15: force CTA size in warps (0 = heuristic) */

@@ -22,6 +22,7 @@ FLAG_GENERIC = 4
 FLAG_AR_DEFERRED = 8
 FLAG_STATIC = 16
 FLAG_HOST_RESULTS = 32
+FLAG_PDL = 64
 FLAG_WARPS_SHIFT = 8
 FLAG_COLS_SHIFT = 16
 STATUS_INVALID_COST = 1

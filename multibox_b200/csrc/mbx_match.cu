@@ -891,9 +891,11 @@ int mbx::match_loss_impl(const mbx_heads *heads, const float *locations, const f
     int nwarps = static_cast<int>((flags >> MBX_FLAG_WARPS_SHIFT) & 0xffu);
     const int ncols = static_cast<int>((flags >> MBX_FLAG_COLS_SHIFT) & 0xffu);
     if (stacked_gt || n_stacked) {
+        p.flags &= ~MBX_FLAG_PDL;   // the scan kernel right before the matching kernel produces one of its inputs
         mbx_scan_num_gt_kernel<<<1, 1024, 0, st>>>(num_gt, gt_row, B, M, p.stk_offsets, n_stacked);
         if (int e = check_cuda(cudaGetLastError(), "launch mbx_scan_num_gt_kernel")) return e;
     }
+    if (flags & MBX_FLAG_GENERIC) p.flags &= ~MBX_FLAG_PDL;   // (the generic kernel has no early-start path)
     if (!(flags & MBX_FLAG_GENERIC)) {
         // register-resident family first; it declines shapes it has no instantiation for
         const int rc = launch_match_reg(p, nwarps, ncols, st);

@@ -70,8 +70,13 @@ struct RSmem {
     double *u, *red;
     int4 *part;                 // [2][NWARPS] {key_hi, key_lo, payload | tie << 31, bits of the unassigned minimum}
     unsigned long long *pk;     // [NWARPS]
-    unsigned long long *rmin;   // [M] first step: min over candidates of (ord32(cost) << 32 | column)
-    unsigned long long *rmax;   // [M] first step: max over candidates of (~ord32(cost) << 32 | column)
+    // first step, exact results per row: the FIRST candidate column to arrive (rcnt 0 -> 1) stores
+    // (ord32(cost) << 32 | column) into rfirst with a plain store; later ones (rare: the candidate window
+    // of a row usually holds one column) fold into rmin / rmax with 64-bit atomics
+    unsigned long long *rfirst; // [M]
+    unsigned long long *rmin;   // [M] min over the later candidates of (ord32(cost) << 32 | column)
+    unsigned long long *rmax;   // [M] max over the later candidates of (~ord32(cost) << 32 | column)
+    unsigned *rcnt;             // [M] candidates evaluated
     float *rowpart;             // [NWARPS][Mp] per-warp cheap first-step minimum of each row
     float *mw;                  // [NWARPS] per-warp margin of the cheap form
     int *col4row, *rm_col, *rm_idx, *rm_pm, *visit, *ri, *ctl;   // ctl[0] next general row, ctl[1] fast path off
@@ -105,6 +110,7 @@ __host__ __device__ inline size_t rcarve(RSmem *s, unsigned char *base, int P, i
     size_t o_gp = take(sizeof(float4) * Mx, 16);
     size_t o_part = take(sizeof(int4) * 2 * nwarps, 16);
     size_t o_rc = take(sizeof(float2) * Mx, 8);
+    size_t o_rfirst = take(sizeof(unsigned long long) * Mx, 8);
     size_t o_rmin = take(sizeof(unsigned long long) * Mx, 8);
     size_t o_rmax = take(sizeof(unsigned long long) * Mx, 8);
     size_t o_cv = take(sizeof(double) * Pc, 8);
@@ -115,6 +121,7 @@ __host__ __device__ inline size_t rcarve(RSmem *s, unsigned char *base, int P, i
     size_t o_bar = take(8, 8);
     size_t o_rp = take(sizeof(float) * static_cast<size_t>(Mp) * nwarps, 4);
     size_t o_mw = take(sizeof(float) * nwarps, 4);
+    size_t o_rcnt = take(sizeof(unsigned) * Mx, 4);
     size_t o_c4r = take(sizeof(int) * Mx, 4);
     size_t o_rmc = take(sizeof(int) * (M + 2), 4);
     size_t o_rmi = take(sizeof(int) * (M + 2), 4);
@@ -132,6 +139,8 @@ __host__ __device__ inline size_t rcarve(RSmem *s, unsigned char *base, int P, i
         s->gp = reinterpret_cast<float4 *>(base + o_gp);
         s->part = reinterpret_cast<int4 *>(base + o_part);
         s->rc = reinterpret_cast<float2 *>(base + o_rc);
+        s->rfirst = reinterpret_cast<unsigned long long *>(base + o_rfirst);
+        s->rcnt = reinterpret_cast<unsigned *>(base + o_rcnt);
         s->rmin = reinterpret_cast<unsigned long long *>(base + o_rmin);
         s->rmax = reinterpret_cast<unsigned long long *>(base + o_rmax);
         s->u = reinterpret_cast<double *>(base + o_u);
@@ -209,6 +218,23 @@ __device__ __forceinline__ void warp_argmin(unsigned &hi, unsigned &lo, unsigned
     pay = mp;
 }
 
+// First-step result of `row` after pass 2: key = ord32(minimum cost), col = lowest column at the
+// minimum, unique = exactly one column attains it.  No candidate at all: key = 0xffffffff.
+__device__ __forceinline__ void first_step_result(const RSmem &s, int row, unsigned &key, unsigned &col, bool &unique) {
+    const unsigned cnt = s.rcnt[row];
+    unsigned long long k1 = s.rfirst[row];
+    if (cnt == 0u) k1 = ~0ull;
+    unsigned long long k2 = ((k1 >> 32) ^ 0xffffffffull) << 32 | (k1 & 0xffffffffull);
+    if (cnt > 1u) {
+        const unsigned long long m1 = s.rmin[row], m2 = s.rmax[row];
+        k1 = m1 < k1 ? m1 : k1;
+        k2 = m2 > k2 ? m2 : k2;
+    }
+    key = static_cast<unsigned>(k1 >> 32);
+    col = static_cast<unsigned>(k1);
+    unique = cnt != 0u && static_cast<unsigned>(k2) == col;
+}
+
 __device__ __forceinline__ float bound_a(const float4 &l, const float4 &gq, float w) {
     return mbx_bound_a(l.x, l.y, l.z, l.w, gq.x, gq.y, gq.z, gq.w, w);
 }
@@ -255,6 +281,7 @@ __global__ void __launch_bounds__(NWARPS * 32, min_blocks_per_sm<NWARPS, C>())
 mbx_match_loss_reg_kernel(const MatchParams p) {
     constexpr int T = NWARPS * 32;
     static_assert(NWARPS <= 32, "one lane per warp partial");
+    static_assert(C <= 8, "candidate queue entries are row * 8 + c");
     constexpr bool RS = (C <= 3);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RSmem s;
@@ -304,6 +331,23 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     const bool has_poster = p.ar_world > 1 && (p.flags & MBX_FLAG_AR_DEFERRED);
     const int n_work = has_poster ? static_cast<int>(gridDim.x) - 1 : static_cast<int>(gridDim.x);
     const bool is_poster = has_poster && static_cast<int>(blockIdx.x) == n_work;
+    // Programmatic dependent launch (MBX_FLAG_PDL; the launcher sets the stream-serialization attribute):
+    // this grid may start while the preceding kernel of the stream -- the previous training step -- is
+    // still running; the next one may start as soon as every CTA of this grid is running.  The caller
+    // promises that the INPUTS do not come from that preceding kernel; everything this grid shares with
+    // it (outputs, workspace, all-reduce state) is only touched after griddepcontrol.wait, which returns
+    // when the preceding grid has completed and its writes are visible.  So the load, the logs and the
+    // whole assignment solve of step k+1 overlap the tail (epilogue, last-CTA reduction, completion) of
+    // step k and the launch latency in between.  Without the attribute both instructions are no-ops.
+    const bool pdl = (p.flags & MBX_FLAG_PDL) != 0;
+    bool dep_done = !pdl;
+    if (pdl) {
+        asm volatile("griddepcontrol.launch_dependents;");
+        if (is_poster || (logits && p.conf_out)) {   // (these write before the epilogue)
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            dep_done = true;
+        }
+    }
     if (is_poster && warp == 0) ar_post_pending(p);
 
     // Image scheduling.  Static (image = CTA index, stride = resident CTAs) when every image has
@@ -415,6 +459,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             s.col4row[i] = -1;
             s.rmin[i] = ~0ull;
             s.rmax[i] = 0ull;
+            s.rcnt[i] = 0u;
         }
         for (int j = tid; j < P; j += T) {
             s.row4col[j] = -1;
@@ -461,6 +506,36 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             // tie for it, if its lower bound a - m_w [+ G_i - mg_i] does not exceed U, i.e.
             // a <= U + m_w + 2 mg_i (G_i cancels).  Each warp visits only the rows for which its own
             // cheap minimum passes that test, and evaluates cost32() only for the passing columns.
+            // The exact evaluations are queued per LANE while the warp walks its rows (cheap, warp-uniform)
+            // and run afterwards, all lanes of the warp side by side: one cost32() latency per warp instead
+            // of one per visited row.
+            int qe0 = -1, qe1 = -1;   // queued (row * 8 + c); a third candidate of one lane is evaluated on the spot
+            auto eval_exact = [&](int entry) {
+                const int row = entry >> 3, c = entry & 7;
+                float4 l = loc[0];
+                float lcv = lc[0], l1v = l1[0];
+#pragma unroll
+                for (int q2 = 1; q2 < C; ++q2) {
+                    const bool hit = q2 == c;
+                    l.x = hit ? loc[q2].x : l.x;
+                    l.y = hit ? loc[q2].y : l.y;
+                    l.z = hit ? loc[q2].z : l.z;
+                    l.w = hit ? loc[q2].w : l.w;
+                    lcv = hit ? lc[q2] : lcv;
+                    l1v = hit ? l1[q2] : l1v;
+                }
+                const float c32 = cost32(l, s.gt[row], half_alpha, lcv, l1v);
+                ok = ok && (c32 > -CUDART_INF_F);
+                MBX_COUNT(9, 1);
+                const unsigned long long k32 = ord32(c32);
+                const unsigned long long col = static_cast<unsigned>(tid + c * T);
+                if (atomicAdd(&s.rcnt[row], 1u) == 0u) {
+                    s.rfirst[row] = (k32 << 32) | col;
+                } else {
+                    atomicMin(&s.rmin[row], (k32 << 32) | col);
+                    atomicMax(&s.rmax[row], ((k32 ^ 0xffffffffull) << 32) | col);
+                }
+            };
             for (int k0 = 0; k0 < n; k0 += 32) {
                 const int i = k0 + lane;
                 float thr = 0.0f;
@@ -481,21 +556,22 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                     const int row = k0 + bit;
                     const float t = __shfl_sync(0xffffffffu, thr, bit);
                     const float4 gq = s.gp[row];
-                    const float4 g = s.gt[row];
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         if ((invalid_mask >> c) & 1u) continue;
                         if (bound_a(loc[c], gq, wq[c]) > t) continue;   // (a NaN bound fails the test: evaluated)
-                        const float c32 = cost32(loc[c], g, half_alpha, lc[c], l1[c]);
-                        ok = ok && (c32 > -CUDART_INF_F);
-                        MBX_COUNT(9, 1);
-                        const unsigned long long k32 = ord32(c32);
-                        const unsigned col = static_cast<unsigned>(tid + c * T);
-                        atomicMin(&s.rmin[row], (k32 << 32) | col);
-                        atomicMax(&s.rmax[row], ((k32 ^ 0xffffffffull) << 32) | col);
+                        const int entry = row * 8 + c;
+                        if (qe0 < 0)
+                            qe0 = entry;
+                        else if (qe1 < 0)
+                            qe1 = entry;
+                        else
+                            eval_exact(entry);
                     }
                 }
             }
+            if (qe0 >= 0) eval_exact(qe0);
+            if (qe1 >= 0) eval_exact(qe1);
             block_sync<NWARPS>();
             MBX_T(8);   // first step, pass 2 (exact costs of the candidates)
         }
@@ -519,10 +595,9 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                     bool good = false;
                     unsigned col = kColNone, key = 0u;
                     if (row < n) {
-                        const unsigned long long k1 = s.rmin[row], k2 = s.rmax[row];
-                        key = static_cast<unsigned>(k1 >> 32);
-                        col = static_cast<unsigned>(k1);
-                        good = (static_cast<unsigned>(k2) == col) && key < kOrdInf32;   // one column at the minimum, finite
+                        bool unique;
+                        first_step_result(s, row, key, col, unique);
+                        good = unique && key < kOrdInf32;   // one column at the minimum, finite
                         if (good) good = !s.dirty[col] && s.row4col[col] < 0;
                     }
                     // an earlier lane of this round wants the same column -> this row conflicts
@@ -567,9 +642,10 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             // have left behind are formed together with step 1's (`pend0`).
             bool pend0 = false;
             {
-                const unsigned long long k1 = s.rmin[cur], k2 = s.rmax[cur];
-                const unsigned key0 = static_cast<unsigned>(k1 >> 32), col0 = static_cast<unsigned>(k1);
-                if (!vpos && static_cast<unsigned>(k2) == col0 && key0 < kOrdInf32 && !s.dirty[col0]) {
+                unsigned key0, col0;
+                bool unique0;
+                first_step_result(s, cur, key0, col0, unique0);
+                if (!vpos && unique0 && key0 < kOrdInf32 && !s.dirty[col0]) {
                     const int r4c0 = s.row4col[col0];
                     if (r4c0 >= 0) {
                         pend0 = true;
@@ -609,6 +685,13 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                     float a[C];
 #pragma unroll
                     for (int c = 0; c < C; ++c) a[c] = bound_a(loc[c], gq, wq[c]);
+                    // path cost through this row: r = ((mv + C) - uu) - v in fp64, v <= 0.  With base = mv - uu and
+                    // S = |mv| + |uu| (+ |UB|), the fp64 chain differs from base + C by at most 2^-52 (S + |C|): the
+                    // 2^-40 S terms below cover it (for |C| > 2^11 S the comparisons hold trivially).
+                    const float base_up = __double2float_ru(__dsub_rn(mv, uu));
+                    const float base_dn = __double2float_rd(__dsub_rn(mv, uu));
+                    const float S = __fadd_ru(__double2float_ru(fabs(mv)), __double2float_ru(fabs(uu)));
+                    const float krow = __fadd_ru(__fadd_ru(rcst.y, m_w), -rcst.x);   // mg + m_w - G (rounded up)
                     if (first_scan) {
                         // no block-wide bound yet: the cheapest UNASSIGNED column of this warp under the cheap
                         // form bounds the final path cost (the search ends at an unassigned column whose path
@@ -618,36 +701,48 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                         for (int c = 0; c < C; ++c)
                             if (!(((asg | scmask) >> c) & 1u)) am = fminf(am, a[c]);
                         am = warp_min_f32(am);
-                        const float ubc = __fadd_ru(__fadd_ru(am, rcst.x), __fadd_ru(rcst.y, m_w));
-                        double ub = __dadd_rn(__dsub_rn(mv, uu), static_cast<double>(ubc));
-                        ub = __dadd_rn(ub, __dmul_rn(__dadd_rn(__dadd_rn(fabs(mv), fabs(uu)), fabs(static_cast<double>(ubc))),
-                                                     9.094947017729282e-13));   // 2^-40: fp64 rounding of the exact chain
-                        UB = fminf(UB, fminf(__double2float_ru(ub), CUDART_INF_F));   // (NaN -> +inf)
+                        const float ubc = __fadd_ru(__fadd_ru(am, rcst.x), __fadd_ru(rcst.y, m_w));   // >= its exact cost
+                        float ub = __fadd_ru(base_up, ubc);
+                        ub = __fmaf_ru(__fadd_ru(S, fabsf(ubc)), 9.094947017729282e-13f, ub);          // + 2^-40 (...)
+                        UB = fminf(UB, fminf(ub, CUDART_INF_F));   // (NaN -> +inf)
                         first_scan = false;
                     }
-                    // a column whose exact path cost (mv + C) - uu [- v, v <= 0] certainly exceeds UB is skipped:
-                    // C > (UB - mv + uu)(1 + 2^-40) is implied by a > thr (mbx_bound.h; every operation rounds up)
-                    double ct = __dadd_rn(__dsub_rn(static_cast<double>(UB), mv), uu);
-                    ct = __dadd_rn(ct, __dmul_rn(__dadd_rn(__dadd_rn(fabs(static_cast<double>(UB)), fabs(mv)), fabs(uu)),
-                                                 9.094947017729282e-13));
-                    const float thr = __fadd_ru(__fadd_ru(__double2float_ru(ct), -rcst.x), __fadd_ru(rcst.y, m_w));
+                    // a column whose exact path cost certainly exceeds UB is skipped: C > UB - base (+ slack) is
+                    // implied by a > thr (mbx_bound.h; every operation rounds up)
+                    float thr = __fadd_ru(__fsub_ru(UB, base_dn), krow);
+                    thr = __fmaf_ru(__fadd_ru(S, fabsf(UB)), 9.094947017729282e-13f, thr);
                     unsigned cand = 0u;
 #pragma unroll
                     for (int c = 0; c < C; ++c)
                         if (!((scmask >> c) & 1u) && !(a[c] > thr)) cand |= 1u << c;
                     if (vpos) cand |= vnz & ~scmask;
+                    // exact costs of the candidates: every lane takes its lowest pending column, all lanes side by side
+                    while (__any_sync(0xffffffffu, cand != 0u)) {
+                        if (cand != 0u) {
+                            const int c = __ffs(cand) - 1;
+                            cand &= cand - 1u;
+                            float4 l = loc[0];
+                            float lcv = lc[0], l1v = l1[0];
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        if (!((cand >> c) & 1u)) continue;
-                        const float c32 = cost32(loc[c], g, half_alpha, lc[c], l1[c]);
-                        ok = ok && (c32 > -CUDART_INF_F);
-                        MBX_COUNT(9, 1);
-                        const int jc = tid + c * T;
-                        const double r =
-                            __dsub_rn(__dsub_rn(__dadd_rn(mv, static_cast<double>(c32)), uu), cv.get(c, jc, s.cv));
-                        if (r < spc.get(c, jc, s.spc)) {
-                            spc.set(c, jc, s.spc, r);
-                            ptag.set(c, jc, s.pmv, tag);
+                            for (int q2 = 1; q2 < C; ++q2) {
+                                const bool hit = q2 == c;
+                                l.x = hit ? loc[q2].x : l.x;
+                                l.y = hit ? loc[q2].y : l.y;
+                                l.z = hit ? loc[q2].z : l.z;
+                                l.w = hit ? loc[q2].w : l.w;
+                                lcv = hit ? lc[q2] : lcv;
+                                l1v = hit ? l1[q2] : l1v;
+                            }
+                            const float c32 = cost32(l, g, half_alpha, lcv, l1v);
+                            ok = ok && (c32 > -CUDART_INF_F);
+                            MBX_COUNT(9, 1);
+                            const int jc = tid + c * T;
+                            const double r =
+                                __dsub_rn(__dsub_rn(__dadd_rn(mv, static_cast<double>(c32)), uu), cv.get(c, jc, s.cv));
+                            if (r < spc.get(c, jc, s.spc)) {
+                                spc.set(c, jc, s.spc, r);
+                                ptag.set(c, jc, s.pmv, tag);
+                            }
                         }
                     }
                 }
@@ -821,6 +916,10 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
         block_sync<NWARPS>();   // the last walk's row4col / col4row are visible below
 
         // ---- epilogue: mask, matched GT index, loss terms, gradients
+        if (!dep_done) {   // first global write of this CTA: the preceding grid must be complete (see above)
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            dep_done = true;
+        }
         double acc_sq = 0.0, acc_conf = 0.0;
         int n_match = 0;
 #pragma unroll
@@ -904,6 +1003,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
         q = dyn ? s.ctl[2] : q + n_work;
     }
 
+    if (!dep_done) asm volatile("griddepcontrol.wait;" ::: "memory");   // (a CTA that solved no image)
     if (status) atomicOr(p.status, status);
 #ifdef MBX_PHASE_TIMING
     MBX_T(7);   // epilogue
@@ -1003,8 +1103,18 @@ int launch_one(const MatchParams &p, cudaStream_t st) {
         if (int e = launch_order(p.num_gt, p.gt_row, 0, p.B, p.M, p.order, st)) return e;
         pp.dynamic = 1;
     }
-    kern<<<units + (poster ? 1 : 0), NWARPS * 32, smem, st>>>(pp);
-    return check_cuda(cudaGetLastError(), "launch mbx_match_loss_reg_kernel");
+    if (pp.dynamic) pp.flags &= ~MBX_FLAG_PDL;   // (the order kernel right before this one produces an input)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(units + (poster ? 1 : 0));
+    cfg.blockDim = dim3(NWARPS * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pp.flags & MBX_FLAG_PDL) ? 1 : 0;
+    return check_cuda(cudaLaunchKernelEx(&cfg, kern, pp), "launch mbx_match_loss_reg_kernel");
 }
 
 }  // namespace

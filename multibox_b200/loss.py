@@ -45,6 +45,24 @@ def _i32c(t, name):
     return t.contiguous()
 
 
+def _same_device(*tensors):
+    """The device all (non-None) argument tensors live on; mixed devices are an argument error.
+    Every C-ABI launch below runs under `torch.cuda.device(dev)`: the library launches on the CUDA
+    *current* device (its occupancy / shared-memory attribute caches are keyed by it), which need not
+    be the tensors' device in a multi-GPU process."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise TypeError("CUDA tensors expected (there is no CPU path)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError("all tensors of one call must live on one device (got %s and %s)" % (dev, t.device))
+    return dev
+
+
 def raise_for_status(status):
     """Same failures, same exception type as scipy.optimize.linear_sum_assignment."""
     status = int(status)
@@ -70,7 +88,7 @@ def match_loss_raw(locations, confidences, gt_bboxes, num_gt, priors, alpha, fla
     lib = _lib.load()
     B, P = locations.shape[0], locations.shape[1]
     M = gt_bboxes.shape[1]
-    dev = locations.device
+    dev = _same_device(locations, confidences, gt_bboxes, num_gt, priors)
     out = {} if out is None else out
 
     def buf(name, want, shape, dtype):
@@ -98,11 +116,12 @@ def match_loss_raw(locations, confidences, gt_bboxes, num_gt, priors, alpha, fla
             _lib.ptr(mask), _lib.ptr(gt_idx), _lib.ptr(stacked), _lib.ptr(n_stacked),
             _lib.ptr(d_loc), _lib.ptr(d_conf), _lib.ptr(conf_out), _lib.ptr(results),
             _lib.ptr(ws), ws.numel())
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    if peer is not None and peer.world > 1:
-        rc = lib.mbx_match_loss_allreduce(*args, peer.ptr_array, peer.world, peer.rank, stream)
-    else:
-        rc = lib.mbx_match_loss(*args, stream)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if peer is not None and peer.world > 1:
+            rc = lib.mbx_match_loss_allreduce(*args, peer.ptr_array, peer.world, peer.rank, stream)
+        else:
+            rc = lib.mbx_match_loss(*args, stream)
     _lib.check(rc, "mbx_match_loss")
     return out
 
@@ -207,15 +226,22 @@ def pad_ragged_gt(gt_flat, gt_row_offsets, max_num_bboxes):
 
 def match_loss_ragged_raw(locations, confidences, gt_flat, gt_row_offsets, priors, alpha, max_num_bboxes,
                           flags=0, want_mask=False, want_gt_idx=False, want_stacked=False, want_grads=True,
-                          out=None):
+                          out=None, validate_offsets=False):
     """``mbx_match_loss_ragged``: ground truth as CSR (gt_flat [N,4] f32, gt_row_offsets [B+1] int32)
     instead of the zero-padded [B,M,4] block of reference inputs.py:340-348.  `max_num_bboxes` is
-    the per-image capacity M.  Same outputs as match_loss_raw."""
+    the per-image capacity M.  Same outputs as match_loss_raw.  The kernel cannot check the offsets
+    against N (it never sees N): `validate_offsets=True` checks them on the host first (one read-back);
+    the autograd entry point add_loss_ragged does so when validate=True."""
     lib = _lib.load()
     B, P = locations.shape[0], locations.shape[1]
     M = int(max_num_bboxes)
-    dev = locations.device
+    dev = _same_device(locations, confidences, gt_flat, gt_row_offsets, priors)
     out = {} if out is None else out
+    if validate_offsets:
+        off = gt_row_offsets.to(torch.int64).cpu()
+        if off.numel() != B + 1 or int(off[0]) != 0 or int(off[-1]) != gt_flat.shape[0] or bool((off[1:] < off[:-1]).any()):
+            raise ValueError("gt_row_offsets must be %d non-decreasing int32 values from 0 to N=%d"
+                             % (B + 1, gt_flat.shape[0]))
 
     def buf(name, want, shape, dtype):
         if not want:
@@ -236,11 +262,12 @@ def match_loss_ragged_raw(locations, confidences, gt_flat, gt_row_offsets, prior
     results = buf("results", True, (_lib.RESULT_WORDS,), torch.float32)
     ws = _workspace(dev, lib.mbx_match_workspace_bytes(B, P, M))
     gt_arg = gt_flat if N > 0 else torch.zeros((1, 4), dtype=torch.float32, device=dev)
-    rc = lib.mbx_match_loss_ragged(_lib.ptr(locations), _lib.ptr(confidences), _lib.ptr(gt_arg),
-                                   _lib.ptr(gt_row_offsets), _lib.ptr(priors), B, P, M, float(alpha), int(flags),
-                                   _lib.ptr(mask), _lib.ptr(gt_idx), _lib.ptr(stacked), _lib.ptr(n_stacked),
-                                   _lib.ptr(d_loc), _lib.ptr(d_conf), None, _lib.ptr(results),
-                                   _lib.ptr(ws), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        rc = lib.mbx_match_loss_ragged(_lib.ptr(locations), _lib.ptr(confidences), _lib.ptr(gt_arg),
+                                       _lib.ptr(gt_row_offsets), _lib.ptr(priors), B, P, M, float(alpha), int(flags),
+                                       _lib.ptr(mask), _lib.ptr(gt_idx), _lib.ptr(stacked), _lib.ptr(n_stacked),
+                                       _lib.ptr(d_loc), _lib.ptr(d_conf), None, _lib.ptr(results),
+                                       _lib.ptr(ws), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "mbx_match_loss_ragged")
     return out
 
@@ -252,7 +279,8 @@ class _AddLossRagged(torch.autograd.Function):
         B, P = loc.shape[0], loc.shape[1]
         conf = _f32c(confidences, "confidences").view(B, P)
         out = match_loss_ragged_raw(loc, conf, _f32c(gt_flat, "gt_flat"), _i32c(gt_row_offsets, "gt_row_offsets"),
-                                    _f32c(bbox_priors, "bbox_priors"), alpha, M, flags=flags)
+                                    _f32c(bbox_priors, "bbox_priors"), alpha, M, flags=flags,
+                                    validate_offsets=bool(validate))
         res = out["results"]
         if validate:
             raise_for_status(res[2].item())
@@ -330,7 +358,7 @@ def match_loss_heads_raw(head_locations, head_confidences, gt_bboxes, num_gt, pr
     lib = _lib.load()
     hl = [_f32c(t, "head_locations") for t in head_locations]
     hc = [_f32c(t, "head_confidences") for t in head_confidences]
-    dev = hl[0].device
+    dev = _same_device(*(hl + hc + [gt_bboxes, num_gt, gt_row_offsets, priors]))
     out = {} if out is None else out
     dl = dc = None
     if want_grads:
@@ -354,11 +382,12 @@ def match_loss_heads_raw(head_locations, head_confidences, gt_bboxes, num_gt, pr
     out.update(d_head_locations=dl, d_head_confidences=dc, mask=mask, matched_gt_idx=gt_idx, confidences=conf_out,
                results=results)
     ws = _workspace(dev, lib.mbx_match_workspace_bytes(B, P, M))
-    rc = lib.mbx_match_loss_heads(ctypes.byref(hs), _lib.ptr(gt_bboxes), _lib.ptr(num_gt), _lib.ptr(gt_row_offsets),
-                                  _lib.ptr(priors), B, P, M, float(alpha), int(flags),
-                                  _lib.ptr(mask), _lib.ptr(gt_idx), None, None, _lib.ptr(conf_out),
-                                  _lib.ptr(results), _lib.ptr(ws), ws.numel(),
-                                  torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        rc = lib.mbx_match_loss_heads(ctypes.byref(hs), _lib.ptr(gt_bboxes), _lib.ptr(num_gt),
+                                      _lib.ptr(gt_row_offsets), _lib.ptr(priors), B, P, M, float(alpha), int(flags),
+                                      _lib.ptr(mask), _lib.ptr(gt_idx), None, None, _lib.ptr(conf_out),
+                                      _lib.ptr(results), _lib.ptr(ws), ws.numel(),
+                                      torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "mbx_match_loss_heads")
     return out
 
@@ -418,12 +447,18 @@ class MultiboxLossStep:
 
     def __init__(self, B, P, M, priors, alpha, device="cuda", logits=False, want_mask=False,
                  want_stacked=False, warps=0, use_graph=False, peer=None, deferred_allreduce=False,
-                 host_results=False, zero_copy=False):
+                 host_results=False, zero_copy=False, pdl=False):
         self.B, self.P, self.M, self.alpha = B, P, M, float(alpha)
         self.device = torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.flags = _lib.FLAG_LOGITS if logits else 0
+        # pdl: programmatic dependent launch (MBX_FLAG_PDL).  The caller promises that the step's INPUTS are
+        # not produced by the kernel that precedes the step on the stream (true for the pinned host staging
+        # of this object, and for device tensors produced earlier): consecutive steps then overlap -- the
+        # load, logs and solve of step k+1 run while step k finishes -- with identical results.
+        if pdl:
+            self.flags |= _lib.FLAG_PDL
         self.warps = warps
         self.priors = _f32c(torch.as_tensor(priors).to(self.device), "priors")
         self.want_mask, self.want_stacked = want_mask, want_stacked
@@ -507,8 +542,18 @@ class MultiboxLossStep:
         else:
             fn = lib.mbx_match_loss
 
+        dev_index = dev.index
+        cur_dev, set_dev = torch.cuda.current_device, torch.cuda.set_device
+
         def launch(_keep=keep):
-            rc = fn(*args, c.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            prev = cur_dev()
+            if prev != dev_index:        # the library launches on the CUDA current device
+                set_dev(dev_index)
+            try:
+                rc = fn(*args, c.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            finally:
+                if prev != dev_index:
+                    set_dev(prev)
             if rc:
                 _lib.check(rc, "mbx_match_loss")
         return launch
@@ -591,16 +636,12 @@ class MultiboxLossStep:
         buffer (`self.h_in`, or another packed pinned buffer passed as `pinned`)."""
         self._ensure_ready()
         if pinned is not None and pinned is not self.h_in:
-            if self.use_graph:
-                self.h_in.copy_(pinned)          # graphs are bound to h_in; keep semantics identical
-            else:
-                self.d_in.copy_(pinned, non_blocking=True)
-                self._launch()
-                self.h_res.copy_(self.out["results"], non_blocking=True)
-                torch.cuda.current_stream(self.device).synchronize()
-                if validate:
-                    raise_for_status(self.h_res[2].item())
-                return float(self.h_res[0]), float(self.h_res[1])
+            # the launch closure and the graph are bound to this object's own staging buffer (the kernel
+            # reads h_in itself with zero_copy, a copy node reads it otherwise): bring the caller's data
+            # there, in every (use_graph, zero_copy) mode
+            if pinned.numel() != self.h_in.numel() or pinned.dtype != self.h_in.dtype:
+                raise ValueError("pinned must be a packed float32 buffer of %d words" % self.h_in.numel())
+            self.h_in.copy_(pinned)
         if self.host_results:
             self._res_u32[15] = 0
         if self._graph is not None:

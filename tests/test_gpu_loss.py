@@ -176,10 +176,14 @@ def test_dynamic_schedule_matches_static(cuda_device):
 
     st = run(_lib.FLAG_STATIC)
     assert st["results"][2] == 0
+    ns = int(st["n_stacked"][0])
+    assert ns == int(d["num_gt"].sum())
     for _ in range(3):
         dy = run(0)
-        for k in ("mask", "matched_gt_idx", "stacked_gt", "d_locations", "d_confidences"):
+        assert int(dy["n_stacked"][0]) == ns
+        for k in ("mask", "matched_gt_idx", "d_locations", "d_confidences"):
             assert np.array_equal(st[k], dy[k]), k
+        assert np.array_equal(st["stacked_gt"][:ns], dy["stacked_gt"][:ns])      # (rows beyond n_stacked are never written)
         assert np.array_equal(st["results"][:8].view(np.uint32), dy["results"][:8].view(np.uint32))
     # and both agree with the oracle on a sample of images
     sub = slice(0, 64)
@@ -218,3 +222,78 @@ def test_step_object_host_mapped_results(cuda_device, use_graph, zero_copy):
     np.testing.assert_allclose([ll, cl], [ref["location_loss"], ref["confidence_loss"]], rtol=RTOL)
 
 
+
+
+def test_step_pinned_foreign_buffer_all_modes(cuda_device):
+    """step_pinned(pinned=...) with a caller-owned packed pinned buffer: same result as step_host in
+    every (use_graph, zero_copy, host_results) mode (the launch closure / graph is bound to the
+    object's own staging buffer, so the data must be brought there)."""
+    B = 8
+    d0 = synth.make_train_inputs(K=5, B=B, M=20, seed=71)
+    d1 = synth.make_train_inputs(K=5, B=B, M=20, seed=72)
+    ref = np_oracle.add_loss(d1["locations"], d1["confidences"], d1["gt"], d1["num_gt"], d1["priors"], 1000.0)
+    for use_graph in (False, True):
+        for zero_copy in (False, True):
+            for host_results in (False, True):
+                step = loss.MultiboxLossStep(B, 646, 20, d0["priors"], 1000.0, use_graph=use_graph,
+                                             zero_copy=zero_copy, host_results=host_results)
+                step.step_host(d0["locations"], d0["confidences"], d0["gt"], d0["num_gt"])     # stale data in h_in
+                other = torch.empty_like(step.h_in).pin_memory()
+                views = step._views(other)
+                for v, a in zip(views, (d1["locations"], d1["confidences"].reshape(B, -1), d1["gt"], d1["num_gt"])):
+                    v.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+                ll, cl = step.step_pinned(pinned=other)
+                np.testing.assert_allclose([ll, cl], [ref["location_loss"], ref["confidence_loss"]], rtol=RTOL,
+                                           err_msg=str((use_graph, zero_copy, host_results)))
+
+
+def test_programmatic_dependent_launch_is_invisible(cuda_device):
+    """MBX_FLAG_PDL lets step k+1 start while step k is still running and only orders the WRITES: a
+    long run of back-to-back steps over alternating heavy (every image 20 GT boxes) and empty batches --
+    the later step is often the faster one -- must leave exactly the last step's outputs behind, and
+    every intermediate state observed through a stream-ordered copy must be that step's."""
+    B, P, M = 32, 646, 20
+    heavy = synth.make_train_inputs(K=5, B=B, M=M, dist="full", seed=5)
+    light = synth.make_train_inputs(K=5, B=B, M=M, dist="uniform", seed=6)
+    light["num_gt"][:] = 0
+    mid = synth.make_train_inputs(K=5, B=B, M=M, dist="uniform", seed=7)
+    batches = [heavy, light, mid]
+    refs = [np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], 1000.0)
+            for d in batches]
+    step = loss.MultiboxLossStep(B, P, M, heavy["priors"], 1000.0, pdl=True)
+    launches = [step.prepare(dev(d["locations"]), dev(d["confidences"]).view(B, P), dev(d["gt"]), dev(d["num_gt"]))
+                for d in batches]
+    torch.cuda.synchronize()
+    order = [0, 1, 0, 1, 2, 1, 0, 0, 1, 2] * 6
+    snaps = []
+    for k, w in enumerate(order):
+        launches[w]()
+        if k % 7 == 3 or k == len(order) - 1:          # stream-ordered observation of this step's outputs
+            snaps.append((w, step.out["results"].clone(), step.out["d_locations"].clone(),
+                          step.out["d_confidences"].clone()))
+    torch.cuda.synchronize()
+    for w, res, dl, dc in snaps:
+        r = res.cpu().numpy()
+        assert r[2] == 0
+        f64 = r.view(np.float64)[2:4]
+        assert abs(f64[0] - refs[w]["location_loss_f64"]) <= RTOL * abs(refs[w]["location_loss_f64"]) + 1e-30
+        assert abs(f64[1] - refs[w]["confidence_loss_f64"]) <= RTOL * abs(refs[w]["confidence_loss_f64"])
+        np.testing.assert_allclose(dl.cpu().numpy(), refs[w]["d_locations"], rtol=RTOL, atol=0)
+        np.testing.assert_allclose(dc.cpu().numpy().reshape(B, P, 1), refs[w]["d_confidences"], rtol=RTOL, atol=0)
+
+
+def test_wrong_current_device_is_handled(cuda_device):
+    """Tensors on cuda:1 while cuda:0 is current: the wrappers switch the current device
+    for the launch (the C side launches on the current device)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d = synth.make_train_inputs(K=5, B=4, M=20, seed=9)
+    ref = np_oracle.add_loss(d["locations"], d["confidences"], d["gt"], d["num_gt"], d["priors"], 1000.0)
+    one = torch.device("cuda", 1)
+    t = [torch.from_numpy(np.ascontiguousarray(d[k])).to(one) for k in ("locations", "confidences", "gt", "num_gt")]
+    with torch.cuda.device(0):
+        out = loss.match_loss_raw(t[0], t[1].view(4, -1), t[2], t[3], torch.from_numpy(d["priors"]).to(one), 1000.0)
+        torch.cuda.synchronize(one)
+    np.testing.assert_allclose(out["results"][:2].cpu().numpy(), [ref["location_loss"], ref["confidence_loss"]], rtol=RTOL)
+    with pytest.raises(ValueError):
+        loss.match_loss_raw(t[0], t[1].view(4, -1), t[2].to("cuda:0"), t[3], torch.from_numpy(d["priors"]).to(one), 1000.0)
