@@ -61,7 +61,7 @@ def build(force=False, verbose=False, extra_flags=(), lib=None):
     with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
         results = list(ex.map(_compile_one, jobs))
     text = "".join(r[0] for r in results)
-    rc = max(r[1] for r in results)
+    rc = 1 if any(r[1] != 0 for r in results) else 0      # (a compiler killed by a signal returns < 0)
     if rc == 0:
         cmd = [nvcc_path()] + LINK_FLAGS + ["-o", lib] + [j[1] for j in jobs]
         proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -67,13 +67,24 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB
-    try:
-        if _build.needs_build():
-            _build.build()
-    except Exception as e:  # no nvcc on this box: fine if a prebuilt .so travelled with the repo
-        if not os.path.isfile(path):
+    if _build.needs_build():
+        try:
+            _build.nvcc_path()
+            have_nvcc = True
+        except RuntimeError:
+            have_nvcc = False
+        if have_nvcc:
+            # sources are newer than the library and a compiler exists: a compile error must surface,
+            # never be hidden behind a stale binary
+            try:
+                _build.build()
+            except Exception as e:
+                raise MultiboxLibraryError("building libmultibox_b200.so failed (%s); refusing to run a stale or "
+                                           "missing library; there is no CPU fallback" % e)
+        elif not os.path.isfile(path):
             raise MultiboxLibraryError(
-                "libmultibox_b200.so is missing and could not be built (%s); there is no CPU fallback" % e)
+                "libmultibox_b200.so is missing and nvcc is not available; there is no CPU fallback")
+        # (no nvcc on this box and a prebuilt .so travelled with the repo: use it)
     lib = ctypes.CDLL(path)
     lib.mbx_version.restype = _c_int
     lib.mbx_last_error.restype = ctypes.c_char_p

@@ -34,8 +34,9 @@ def filter_proposals(bboxes, confidences, restrictions=None):
     ob = torch.empty_like(b)
     oc = torch.empty_like(c)
     cnt = torch.empty((1,), dtype=torch.int32, device=b.device)
-    rc = lib.mbx_filter_proposals(_lib.ptr(b), _lib.ptr(c), _lib.ptr(r), 1, P, _lib.ptr(ob), _lib.ptr(oc),
-                                  None, _lib.ptr(cnt), _stream(b.device))
+    with torch.cuda.device(b.device):      # the library launches on the CUDA current device
+        rc = lib.mbx_filter_proposals(_lib.ptr(b), _lib.ptr(c), _lib.ptr(r), 1, P, _lib.ptr(ob), _lib.ptr(oc),
+                                      None, _lib.ptr(cnt), _stream(b.device))
     _lib.check(rc, "mbx_filter_proposals")
     n = int(cnt.item())
     if n == 0:
@@ -55,8 +56,9 @@ def filter_proposals_batched(bboxes, confidences, restrictions=None):
     ob, oc = torch.zeros_like(b), torch.zeros_like(c)
     oi = torch.full((B, P), -1, dtype=torch.int32, device=b.device)
     cnt = torch.empty((B,), dtype=torch.int32, device=b.device)
-    rc = lib.mbx_filter_proposals(_lib.ptr(b), _lib.ptr(c), _lib.ptr(r), B, P, _lib.ptr(ob), _lib.ptr(oc),
-                                  _lib.ptr(oi), _lib.ptr(cnt), _stream(b.device))
+    with torch.cuda.device(b.device):      # the library launches on the CUDA current device
+        rc = lib.mbx_filter_proposals(_lib.ptr(b), _lib.ptr(c), _lib.ptr(r), B, P, _lib.ptr(ob), _lib.ptr(oc),
+                                      _lib.ptr(oi), _lib.ptr(cnt), _stream(b.device))
     _lib.check(rc, "mbx_filter_proposals")
     return ob, oc, oi, cnt
 
@@ -76,10 +78,24 @@ def convert_proposals(bboxes, offset, patch_dims, image_dims, is_flipped=0):
                          dtype=torch.int32).to(dev)
     out = torch.empty((1, K, 4), dtype=torch.float64, device=dev)
     off, pd, imd = i2(offset), i2(patch_dims), i2(image_dims)   # keep alive until the launch is enqueued
-    rc = lib.mbx_convert_proposals(_lib.ptr(b), _lib.ptr(off), _lib.ptr(pd), _lib.ptr(imd), _lib.ptr(fl),
-                                   None, 1, K, _lib.ptr(out), _stream(dev))
+    with torch.cuda.device(dev):      # the library launches on the CUDA current device
+        rc = lib.mbx_convert_proposals(_lib.ptr(b), _lib.ptr(off), _lib.ptr(pd), _lib.ptr(imd), _lib.ptr(fl),
+                                       None, 1, K, _lib.ptr(out), _stream(dev))
     _lib.check(rc, "mbx_convert_proposals")
     return out[0]
+
+
+K_MAX_LIMIT = 1024      # detections one CTA can sort / suppress (mbx_detect returns MBX_E_TOO_LARGE beyond it)
+
+
+def _check_k_max(k_max):
+    """The reference has no cap on max_to_keep; this kernel family does (1024 per image / patch).  A
+    larger request is an argument error, never a silent clamp."""
+    k_max = int(k_max)
+    if k_max > K_MAX_LIMIT:
+        raise _lib.MultiboxLibraryError("k_max / max_to_keep = %d exceeds the %d detections per image this "
+                                        "kernel supports (MBX_E_TOO_LARGE)" % (k_max, K_MAX_LIMIT))
+    return max(1, k_max)
 
 
 def postprocess(locs, confs, bbox_priors, restrictions=None, max_to_keep=None, offsets=None,
@@ -107,7 +123,7 @@ def postprocess(locs, confs, bbox_priors, restrictions=None, max_to_keep=None, o
         if mk is None:
             raise ValueError("postprocess needs k_max or max_to_keep")
         k_max = int(mk.max().item())
-    k_max = max(1, min(int(k_max), 1024))
+    k_max = _check_k_max(k_max)
     conv = [offsets, patch_dims, image_dims]
     if any(c is not None for c in conv) and not all(c is not None for c in conv):
         raise ValueError("offsets, patch_dims and image_dims must be given together")
@@ -130,11 +146,12 @@ def postprocess(locs, confs, bbox_priors, restrictions=None, max_to_keep=None, o
     idx = buf("prior_idx", (B, k_max), torch.int32)
     cnt = buf("count", (B,), torch.int32)
     flags = (_lib.FLAG_LOGITS if logits else 0) | (int(warps) << _lib.FLAG_WARPS_SHIFT)
-    rc = lib.mbx_detect(_lib.ptr(loc), _lib.ptr(conf), _lib.ptr(pri), _lib.ptr(r), _lib.ptr(mk),
-                        _lib.ptr(off), _lib.ptr(pd), _lib.ptr(imd), _lib.ptr(fl),
-                        B, P, k_max, -1.0 if nms_iou is None else float(nms_iou), flags,
-                        _lib.ptr(boxes), _lib.ptr(pboxes), _lib.ptr(scores), _lib.ptr(idx), _lib.ptr(cnt),
-                        None, 0, _stream(dev))
+    with torch.cuda.device(dev):      # the library launches on the CUDA current device
+        rc = lib.mbx_detect(_lib.ptr(loc), _lib.ptr(conf), _lib.ptr(pri), _lib.ptr(r), _lib.ptr(mk),
+                            _lib.ptr(off), _lib.ptr(pd), _lib.ptr(imd), _lib.ptr(fl),
+                            B, P, k_max, -1.0 if nms_iou is None else float(nms_iou), flags,
+                            _lib.ptr(boxes), _lib.ptr(pboxes), _lib.ptr(scores), _lib.ptr(idx), _lib.ptr(cnt),
+                            None, 0, _stream(dev))
     _lib.check(rc, "mbx_detect")
     return out
 
@@ -161,7 +178,7 @@ def postprocess_heads(head_locations, head_confidences, bbox_priors, restriction
         if mk is None:
             raise ValueError("postprocess_heads needs k_max or max_to_keep")
         k_max = int(mk.max().item())
-    k_max = max(1, min(int(k_max), 1024))
+    k_max = _check_k_max(k_max)
     conv = [offsets, patch_dims, image_dims]
     if any(c is not None for c in conv) and not all(c is not None for c in conv):
         raise ValueError("offsets, patch_dims and image_dims must be given together")
@@ -177,11 +194,12 @@ def postprocess_heads(head_locations, head_confidences, bbox_priors, restriction
     if want_patch_boxes:
         pboxes = out["patch_boxes"] = torch.empty((B, k_max, 4), dtype=torch.float32, device=dev)
     flags = (_lib.FLAG_LOGITS if logits else 0) | (int(warps) << _lib.FLAG_WARPS_SHIFT)
-    rc = lib.mbx_detect_heads(ctypes.byref(hs), _lib.ptr(pri), _lib.ptr(r), _lib.ptr(mk),
-                              _lib.ptr(off), _lib.ptr(pd), _lib.ptr(imd), _lib.ptr(fl),
-                              B, P, k_max, -1.0 if nms_iou is None else float(nms_iou), flags,
-                              _lib.ptr(out["boxes"]), _lib.ptr(pboxes), _lib.ptr(out["scores"]),
-                              _lib.ptr(out["prior_idx"]), _lib.ptr(out["count"]), None, 0, _stream(dev))
+    with torch.cuda.device(dev):      # the library launches on the CUDA current device
+        rc = lib.mbx_detect_heads(ctypes.byref(hs), _lib.ptr(pri), _lib.ptr(r), _lib.ptr(mk),
+                                  _lib.ptr(off), _lib.ptr(pd), _lib.ptr(imd), _lib.ptr(fl),
+                                  B, P, k_max, -1.0 if nms_iou is None else float(nms_iou), flags,
+                                  _lib.ptr(out["boxes"]), _lib.ptr(pboxes), _lib.ptr(out["scores"]),
+                                  _lib.ptr(out["prior_idx"]), _lib.ptr(out["count"]), None, 0, _stream(dev))
     _lib.check(rc, "mbx_detect_heads")
     return out
 
@@ -192,17 +210,22 @@ def nms(boxes, scores, iou_threshold, max_keep=None, counts=None):
     the kernel clips to that range), scores [B,n] f32, optional counts [B] (valid boxes per row;
     the rest is ignored).  Boxes are visited in descending score order (ties: higher index first)
     and a box is dropped when an already kept one overlaps it with IoU > iou_threshold (strict,
-    fp32, torchvision's CPU arithmetic).  Only the top `max_keep` (default min(n, 1024)) by score
-    enter the suppression.  Returns (keep_idx i32 [B,k] padded with -1, count i32 [B])."""
+    fp32, torchvision's CPU arithmetic).  The top min(n, 1024) boxes by score enter the suppression
+    (the kernel's per-image capacity; documented limit, the rest is dropped); `max_keep` truncates the
+    KEPT list afterwards.  Returns (keep_idx i32 [B,k] padded with -1, count i32 [B])."""
     b = _f32c(boxes, "boxes")
     B, n = b.shape[0], b.shape[1]
     s = _f32c(scores, "scores").view(B, n)
     if counts is not None:
         valid = torch.arange(n, device=b.device).view(1, n) < counts.view(B, 1)
         s = torch.where(valid, s, torch.full_like(s, float("-inf")))
-    k = min(n, 1024) if max_keep is None else max(1, min(int(max_keep), 1024))
+    k = max(1, min(n, K_MAX_LIMIT))
     out = postprocess(b, s.view(B, n, 1), None, nms_iou=float(iou_threshold), k_max=k, want_patch_boxes=False)
-    return out["prior_idx"], out["count"]
+    idx, cnt = out["prior_idx"], out["count"]
+    if max_keep is not None and int(max_keep) < k:
+        idx = idx[:, :max(1, int(max_keep))].contiguous()
+        cnt = torch.clamp(cnt, max=max(1, int(max_keep)))
+    return idx, cnt
 
 
 def detection_results(post, image_ids):
@@ -317,12 +340,13 @@ class DetectStep:
             hv = lambda n: self.view_in(self.h_in, n).data_ptr()   # noqa: E731
             ho = self.views_out(self.h_out)
             flags = (_lib.FLAG_LOGITS if self.logits else 0) | (int(self.warps) << _lib.FLAG_WARPS_SHIFT)
-            rc = lib.mbx_detect(hv("locations"), hv("confidences"), self.priors.data_ptr(), hv("restrictions"),
-                                hv("max_to_keep"), hv("offsets"), hv("patch_dims"), hv("image_dims"),
-                                hv("is_flipped"), B, P, self.k,
-                                -1.0 if self.nms_iou is None else float(self.nms_iou), flags,
-                                ho["boxes"].data_ptr(), None, ho["scores"].data_ptr(), ho["prior_idx"].data_ptr(),
-                                ho["count"].data_ptr(), None, 0, _stream(self.device))
+            with torch.cuda.device(self.device):      # the library launches on the CUDA current device
+                rc = lib.mbx_detect(hv("locations"), hv("confidences"), self.priors.data_ptr(), hv("restrictions"),
+                                    hv("max_to_keep"), hv("offsets"), hv("patch_dims"), hv("image_dims"),
+                                    hv("is_flipped"), B, P, self.k,
+                                    -1.0 if self.nms_iou is None else float(self.nms_iou), flags,
+                                    ho["boxes"].data_ptr(), None, ho["scores"].data_ptr(), ho["prior_idx"].data_ptr(),
+                                    ho["count"].data_ptr(), None, 0, _stream(self.device))
             _lib.check(rc, "mbx_detect")
             return
         self.d_in.copy_(self.h_in, non_blocking=True)

@@ -104,7 +104,11 @@ class PeerAllreduce:
     def __init__(self, group=None, device=None):
         import ctypes
         from . import _lib
-        self.rank, self.world = world()
+        if is_dist():        # rank / size INSIDE the group the buffers are exchanged over
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self.group = group
         self.ptr_array = None
         self._keep = None
         if self.world == 1:
@@ -124,3 +128,16 @@ class PeerAllreduce:
         assert len(ptrs) == self.world
         self.ptr_array = (ctypes.c_ulonglong * self.world)(*ptrs)
         self._keep = (buf, hdl)
+
+    def reset(self):
+        """Collective: re-zeroes every rank's symmetric buffer (step counters, arrival counters, slot
+        ring).  Call on ALL ranks after a step reported MBX_STATUS_AR_TIMEOUT -- the ranks' counters are
+        out of step after a timeout and every later reduction would stay wrong -- with no step in flight."""
+        if self.world == 1:
+            return
+        buf = self._keep[0]
+        torch.cuda.synchronize(buf.device)
+        dist.barrier(self.group)
+        buf.zero_()
+        torch.cuda.synchronize(buf.device)
+        dist.barrier(self.group)

@@ -631,6 +631,31 @@ class MultiboxLossStep:
         np.copyto(self.h_ng.numpy(), num_gt)
         return self.step_pinned(validate)
 
+    def submit_pinned(self):
+        """Enqueues the step on the data currently in the pinned staging buffer and returns at once;
+        `wait()` later returns its losses.  With two step objects a caller keeps TWO steps in flight:
+        stage + submit step k+1 while the GPU runs step k, then wait for k (bench.py's e2e loop)."""
+        self._ensure_ready()
+        if self.host_results:
+            self._res_u32[15] = 0
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._enqueue_host_step()
+
+    def wait(self, validate=True):
+        """Completes the step enqueued by submit_pinned: (location_loss, confidence_loss)."""
+        if self.host_results:
+            self._wait_host_results()
+            r = self._res_f32
+            if validate and r[2] != 0.0:
+                raise_for_status(float(r[2]))
+            return float(r[0]), float(r[1])
+        torch.cuda.current_stream(self.device).synchronize()
+        if validate:
+            raise_for_status(self.h_res[2].item())
+        return float(self.h_res[0]), float(self.h_res[1])
+
     def step_pinned(self, validate=True, pinned=None):
         """Same as step_host when the caller already wrote into the pinned staging
         buffer (`self.h_in`, or another packed pinned buffer passed as `pinned`)."""
@@ -642,19 +667,5 @@ class MultiboxLossStep:
             if pinned.numel() != self.h_in.numel() or pinned.dtype != self.h_in.dtype:
                 raise ValueError("pinned must be a packed float32 buffer of %d words" % self.h_in.numel())
             self.h_in.copy_(pinned)
-        if self.host_results:
-            self._res_u32[15] = 0
-        if self._graph is not None:
-            self._graph.replay()
-        else:
-            self._enqueue_host_step()
-        if self.host_results:
-            self._wait_host_results()
-            r = self._res_f32
-            if validate and r[2] != 0.0:
-                raise_for_status(float(r[2]))
-            return float(r[0]), float(r[1])
-        torch.cuda.current_stream(self.device).synchronize()
-        if validate:
-            raise_for_status(self.h_res[2].item())
-        return float(self.h_res[0]), float(self.h_res[1])
+        self.submit_pinned()
+        return self.wait(validate)

@@ -101,9 +101,11 @@ def merge_patches(post, image_index, num_images, nms_iou=0.5, max_detections=200
     coordinates, scores [Bp,k], count [Bp]); image_index int [Bp]: the image each patch belongs to
     (0 <= . < num_images, patches of an image in any order).  Per image: candidates in (patch
     order, rank) order, sorted by descending score (ties: later candidate first, the kernel's
-    documented tie rule), greedy NMS at `nms_iou` on the float32 boxes (None = no NMS), at most
-    `max_detections` kept.  Returns boxes f64 [I,kmax,4] (the patches' float64 values, gathered),
-    scores f32 [I,kmax], source_patch i32 [I,kmax] (-1 padding), count i32 [I].  No sync."""
+    documented tie rule), greedy NMS at `nms_iou` on the float32 boxes (None = no NMS) over the pooled
+    candidates -- the top 1024 by score when an image has more, the kernel's per-image capacity -- and
+    the first `max_detections` of the KEPT list are returned.  Returns boxes f64 [I,kmax,4] (the
+    patches' float64 values, gathered), scores f32 [I,kmax], source_patch i32 [I,kmax] (-1 padding),
+    count i32 [I].  One host read-back (the largest per-image candidate count sizes the pooled buffer)."""
     boxes, scores, count = post["boxes"], post["scores"], post["count"]
     dev = boxes.device
     Bp, k = scores.shape
@@ -129,11 +131,13 @@ def merge_patches(post, image_index, num_images, nms_iou=0.5, max_detections=200
     cand_boxes64[flat] = boxes[valid]
     cand_scores[flat] = scores[valid]
     cand_patch[flat] = torch.arange(Bp, device=dev, dtype=torch.int32).view(Bp, 1).expand(Bp, k)[valid]
-    kmax = max(1, min(int(max_detections), 1024))
+    kpool = max(1, min(Pm, detect.K_MAX_LIMIT))          # candidates that enter the suppression
+    kmax = max(1, min(int(max_detections), kpool))
     # empty slots carry a -inf score: mbx_detect never takes them as proposals; priors=None: identity decode
     merged = detect.postprocess(cand_boxes64.view(num_images, Pm, 4).to(torch.float32),
-                                cand_scores.view(num_images, Pm, 1), None, nms_iou=nms_iou, k_max=kmax,
+                                cand_scores.view(num_images, Pm, 1), None, nms_iou=nms_iou, k_max=kpool,
                                 want_patch_boxes=False)
+    merged = {k: (v[:, :kmax].contiguous() if v.dim() > 1 else torch.clamp(v, max=kmax)) for k, v in merged.items()}
     pi = merged["prior_idx"].to(torch.int64).clamp_(min=0)
     kept = merged["prior_idx"] >= 0
     out_boxes = torch.gather(cand_boxes64.view(num_images, Pm, 4), 1, pi.unsqueeze(-1).expand(-1, -1, 4))
