@@ -9,11 +9,16 @@ loss forward/backward) over one batch of synthetic head outputs.  The N=1
 workload is BASELINE.json configs[1]: Inception-ResNet-v2-shaped head outputs,
 5 aspect ratios (P=646 priors), batch 32, MAX_NUM_BBOXES=20.  With N>1 every rank
 runs the same per-GPU batch (weak scaling; images are independent) and the two
-loss scalars are SUM-all-reduced over NCCL every step.  Rank 0 prints ONE JSON line.
-A second object in the same line ("detect") reports BASELINE.json configs[2]
-(decode + top-k + NMS, batch 256) and "throughput_shape" reports a
-configs[4]-shaped per-GPU shard where the kernel is throughput- rather than
-launch-bound.
+loss scalars are SUM-all-reduced every step (fused into the kernel over NVLink
+peer memory, checked against an NCCL all-reduce after the timed region).  Rank 0
+prints ONE JSON line.  Further objects in the same line:
+  "serialized"         the same steps without programmatic dependent launch
+  "detect"             BASELINE configs[2] (decode + top-k + NMS, batch 256) [+ the detection all-gather at N>1]
+  "strong_cfg3"        BASELINE configs[3] as written: batch 1024 TOTAL, sharded by image over the N GPUs
+  "coco_person_shape"  the same shape, 1024 images per GPU (weak)
+  "throughput_shape"   a BASELINE configs[4] per-GPU shard of the training step (K=11, M=200, 1024 images)
+  "cfg5_detect"        the configs[4] detect leg (K=11, 1024 images per GPU, NMS 0.5)
+  "layouts"            per-head / ragged entry points against the un-fused route
 """
 import argparse
 import json
@@ -50,6 +55,31 @@ def traffic_from_profiles(kernel):
             return e["dram_bytes_per_launch"] if isinstance(e, dict) else e
     except Exception:
         return None
+
+
+def counters_from_profiles(key):
+    """Per-launch ncu counters (warp instructions executed, DRAM bytes) of the committed capture of this
+    workload (profiles/ncu_counters.json), for the issue-slot roofline."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_counters.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
+def issue_roofline(key, kernel_s, sm_mhz, sms=148):
+    """Issue-slot roofline of the dominant kernel: warp instructions per launch (ncu smsp__inst_executed.sum of
+    the committed capture) / (SMs x 4 schedulers x clock x kernel time).  This, not HBM, is the bound the
+    assignment solver runs against."""
+    c = counters_from_profiles(key)
+    if not c or not kernel_s:
+        return None
+    mhz = sm_mhz or 1965.0
+    peak = sms * 4 * mhz * 1e6              # warp instructions / s
+    ach = c["warp_inst_per_launch"] / kernel_s
+    return {"bound": "issue", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s", "frac": ach / peak,
+            "warp_inst_per_launch": c["warp_inst_per_launch"], "sm_mhz": mhz,
+            "source": "profiles/ncu_counters.json (%s)" % c.get("capture", "ncu --set full")}
 
 
 class ClockSampler:
@@ -183,25 +213,50 @@ def cpu_baseline_detect(q, budget_s=6.0, nms=0.5):
             "sample": "%d passes over the first %d images of the batch (numpy oracle port)" % (n, sub)}
 
 
+def _cpu_detect_shard(args):
+    lo, hi = args
+    q = _REF_Q
+    from oracle import np_oracle
+    sub = [q[k][lo:hi] for k in ("locations", "confidences")] + [q["priors"]] + \
+        [q[k][lo:hi] for k in ("restrictions", "max_to_keep", "offsets", "patch_dims", "image_dims", "is_flipped")]
+    out = np_oracle.postprocess(*sub, nms_iou=q["nms_iou"])
+    return int(np.asarray(out["count"]).sum())
+
+
+_REF_Q = None
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (the
     oracle port: numpy + scipy restatement with the reference's loops) on all
-    host cores, sharded by image across processes."""
+    host cores, sharded by image across processes.  Each step processes the SAME GLOBAL batch the GPU
+    arm processes at this N (32 images per GPU x N)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import multiprocessing as mp
     from multibox_b200 import synth
+    N = max(1, args.gpus)
     cfg = dict(synth.TRAIN_CONFIGS["cfg2"])
-    d = synth.make_train_inputs(**cfg)
+    parts = []
+    for r in range(N):                      # the N ranks' batches (same seeds as the GPU arm)
+        c = dict(cfg)
+        c["seed"] = cfg["seed"] + 7919 * r
+        parts.append(synth.make_train_inputs(**c))
+    d = dict(parts[0])
+    for k in ("locations", "confidences", "gt", "num_gt"):
+        d[k] = np.concatenate([q[k] for q in parts], 0)
+    d["B"] = parts[0]["B"] * N
     B = d["B"]
     cores = max(1, min(os.cpu_count() or 1, B))
     try:
         cores = min(cores, len(os.sched_getaffinity(0)))
     except Exception:
         pass
-    global _REF_D
+    global _REF_D, _REF_Q
     _REF_D = d
+    qcfg = dict(synth.DETECT_CONFIGS["cfg3"])
+    _REF_Q = synth.make_detect_inputs(**qcfg)
     bounds = [((B * i) // cores, (B * (i + 1)) // cores) for i in range(cores)]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
@@ -211,16 +266,33 @@ def run_reference(args):
         for _ in range(args.steps):
             pool.map(_cpu_train_shard, bounds)
         el = time.perf_counter() - t0
+        # detect leg (BASELINE configs[2]): a bounded sample of the 256-image batch, all cores
+        QB = _REF_Q["B"]
+        sub = min(QB, 4 * cores)
+        qb = [((sub * i) // cores, (sub * (i + 1)) // cores) for i in range(cores)]
+        pool.map(_cpu_detect_shard, qb)
+        dn, t1 = 0, time.perf_counter()
+        while time.perf_counter() - t1 < 8.0:
+            pool.map(_cpu_detect_shard, qb)
+            dn += 1
+        del_ = time.perf_counter() - t1
     value = B * args.steps / el
+    dval = sub * dn / del_
     line = {
         "impl": "reference", "metric": "match+loss images/sec", "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": train_config_dict(d, args.gpus, cold="n/a (CPU)"),
+        "config": train_config_dict(parts[0], args.gpus, cold="n/a (CPU)"),
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": "each step = the full %d-image batch, sharded by image over %d processes; "
-                                   "numpy/scipy oracle port of reference loss.py:8-117" % (B, cores)},
+                         "sample": "each step = the full global batch of %d images (%d per GPU x %d), sharded by "
+                                   "image over %d processes; numpy/scipy oracle port of reference loss.py:8-117"
+                                   % (B, parts[0]["B"], N, cores)},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "detect": {"metric": "decode+NMS images/sec", "value": dval, "unit": "images/s",
+                   "cpu_baseline": {"value": dval, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": "%d passes over the first %d images of the configs[2] batch, sharded "
+                                              "over %d processes; numpy port of reference detect.py:408-436 + the "
+                                              "project's greedy NMS (IoU 0.5)" % (dn, sub, cores)}},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -262,7 +334,8 @@ def time_region(fn, steps, warmup, barrier):
     return e0.elapsed_time(e1) / 1e3
 
 
-def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True):
+def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True, check_allreduce=False):
+    """Device-resident steps (value) and host-buffer steps (e2e) of match + loss fwd/bwd on batch `d`."""
     import torch
     from multibox_b200 import loss
     B, P, M = d["B"], d["P"], d["M"]
@@ -287,47 +360,87 @@ def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True)
         launches[i % nsets]()
 
     sec = time_region(one, steps, warmup, barrier)
-    # kernel-only duration of the dominant kernel, live, with events around each launch
-    kt = []
-    for i in range(min(steps, 50)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        launches[(warmup + steps + i) % nsets]()
-        b.record()
-        kt.append((a, b))
-    torch.cuda.synchronize()
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kt]))
-    res = {"sec": sec, "kernel_ms": kernel_ms, "nsets": nsets, "launches_per_step": 1}
+    res = {"sec": sec, "nsets": nsets, "launches_per_step": 1}
+    if check_allreduce and world > 1:
+        # the fused all-reduce against NCCL on the same step: complete the newest step's reduction
+        # (deferred mode), then SUM-all-reduce the local fp64 sums of that step over NCCL
+        import torch.distributed as dist
+        g = step.flush()
+        local = step.out["results"].to(dev).view(torch.float64)[2:4].clone()
+        dist.all_reduce(local, op=dist.ReduceOp.SUM)
+        want = [float(x) for x in local.cpu()]
+        ok = all(abs(a - b) <= 1e-12 * max(1.0, abs(b)) for a, b in zip(g, want))
+        res["allreduce_check"] = "ok" if ok else "MISMATCH fused=%r nccl=%r" % (list(g), want)
     if want_e2e:
-        # host path: rotate over several packed pinned input sets (each its own step object /
-        # CUDA graph) so the H2D source is not one hot buffer either
+        # host path.  Four step objects (own pinned staging buffer, own mapped result block, own gradients)
+        # rotate, so the H2D source is not one hot buffer; the kernel streams the packed pinned inputs
+        # over PCIe itself (zero_copy) and stores the 64-byte result block into mapped host memory.
         hsets = 4
-        hsteps = []
-        for r in range(hsets):
-            hs = loss.MultiboxLossStep(B, P, M, d["priors"], d["alpha"], device=dev, use_graph=True, peer=peer,
-                                       deferred_allreduce=True, host_results=True, zero_copy=True)
-            np.copyto(hs.h_loc.numpy(), np.roll(d["locations"], r, axis=0))
-            np.copyto(hs.h_conf.numpy(), np.roll(d["confidences"].reshape(B, P), r, axis=0))
-            np.copyto(hs.h_gt.numpy(), np.roll(d["gt"], r, axis=0))
-            np.copyto(hs.h_ng.numpy(), np.roll(d["num_gt"], r, axis=0))
-            hsteps.append(hs)
+        roll = [dict(locations=np.roll(d["locations"], r, axis=0),
+                     confidences=np.roll(d["confidences"].reshape(B, P), r, axis=0),
+                     gt=np.roll(d["gt"], r, axis=0), num_gt=np.roll(d["num_gt"], r, axis=0)) for r in range(hsets)]
+
+        def make(use_graph, use_pdl):
+            out = []
+            for r in range(hsets):
+                hs = loss.MultiboxLossStep(B, P, M, d["priors"], d["alpha"], device=dev, use_graph=use_graph, peer=peer,
+                                           deferred_allreduce=True, host_results=True, zero_copy=True, pdl=use_pdl)
+                stage(hs, r)
+                out.append(hs)
+            return out
+
+        def stage(hs, r):
+            np.copyto(hs.h_loc.numpy(), roll[r]["locations"])
+            np.copyto(hs.h_conf.numpy(), roll[r]["confidences"])
+            np.copyto(hs.h_gt.numpy(), roll[r]["gt"])
+            np.copyto(hs.h_ng.numpy(), roll[r]["num_gt"])
+
+        def wall(fn, n, drain=None):
+            for i in range(max(warmup, hsets)):
+                fn(i)
+            if drain:
+                drain()
+            barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(n):
+                fn(max(warmup, hsets) + i)
+            if drain:
+                drain()
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0
+
         last = {}
+        # (a) one step in flight: submit, poll, next (the round-1 mode; CUDA graph of the one kernel)
+        ser = make(True, False)
 
-        def e2e_step(i):
-            hs = hsteps[i % hsets]
-            last["v"] = hs.step_pinned(validate=True)     # graph: H2D, kernel (+fused all-reduce), D2H; sync
+        def e2e_serial(i):
+            last["v"] = ser[i % hsets].step_pinned(validate=True)
 
-        for i in range(max(warmup, hsets)):
-            e2e_step(i)
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(steps):
-            e2e_step(max(warmup, hsets) + i)
-        torch.cuda.synchronize()
-        el = time.perf_counter() - t0
-        res.update(e2e_sec=el, h2d=hsteps[0].h2d_bytes, d2h=hsteps[0].d2h_bytes, last=last["v"],
-                   last_global=hsteps[(max(warmup, hsets) + steps - 1) % hsets].flush())
+        res["e2e_serial_sec"] = wall(e2e_serial, steps)
+        res["last"] = last["v"]
+        res["last_global"] = ser[(max(warmup, hsets) + steps - 1) % hsets].flush()
+        # (b) TWO steps in flight: step k+1 is submitted (its zero-copy PCIe reads and its solve overlap the
+        # tail of step k: programmatic dependent launch) before the host polls step k's result block
+        pipe = make(False, True)
+        pend = []
+
+        def e2e_pipe(i, numpy_in=False):
+            hs = pipe[i % hsets]
+            if numpy_in:                      # a caller that holds plain numpy arrays pays this staging copy
+                stage(hs, i % hsets)
+            hs.submit_pinned()
+            pend.append(hs)
+            if len(pend) > 1:
+                last["p"] = pend.pop(0).wait(validate=True)
+
+        def drain():
+            while pend:
+                last["p"] = pend.pop(0).wait(validate=True)
+
+        res["e2e_sec"] = wall(e2e_pipe, steps, drain)
+        res["e2e_numpy_in_sec"] = wall(lambda i: e2e_pipe(i, True), steps, drain)
+        res.update(h2d=pipe[0].h2d_bytes, d2h=pipe[0].d2h_bytes, last_pipe=last["p"])
     return res
 
 
@@ -373,7 +486,7 @@ def bench_layouts(d, barrier, steps=20, warmup=3):
     return res
 
 
-def bench_detect(q, steps, warmup, barrier, nms_iou, want_e2e=True, zero_copy=False):
+def bench_detect(q, steps, warmup, barrier, nms_iou, want_e2e=True, zero_copy=False, world=1):
     import torch
     from multibox_b200 import detect
     B, P, keep = q["B"], q["P"], q["keep"]
@@ -392,18 +505,25 @@ def bench_detect(q, steps, warmup, barrier, nms_iou, want_e2e=True, zero_copy=Fa
         detect.postprocess(sets["locations"][s], sets["confidences"][s], pri, restrictions=sets["restrictions"][s],
                            max_to_keep=sets["max_to_keep"][s], offsets=sets["offsets"][s],
                            patch_dims=sets["patch_dims"][s], image_dims=sets["image_dims"][s],
-                           is_flipped=sets["is_flipped"][s], nms_iou=nms_iou, k_max=keep, out=out)
+                           is_flipped=sets["is_flipped"][s], nms_iou=nms_iou, k_max=keep, want_patch_boxes=False,
+                           out=out)
 
     sec = time_region(one, steps, warmup, barrier)
-    kt = []
-    for i in range(min(steps, 50)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        one(warmup + steps + i)
-        b.record()
-        kt.append((a, b))
-    torch.cuda.synchronize()
-    res = {"sec": sec, "kernel_ms": float(np.mean([a.elapsed_time(b) for a, b in kt])), "nsets": nsets}
+    res = {"sec": sec, "kernel_ms": 1e3 * sec / steps, "nsets": nsets}
+    if world > 1:
+        # the final detection gather (north star): every rank's padded detections all-gathered over NCCL
+        # (NVLink) after its kernel, every step, inside the timed region
+        from multibox_b200 import dist as mdist
+        gathered = {}
+
+        def one_gather(i):
+            one(i)
+            gathered["g"] = mdist.gather_detections({k: out[k] for k in ("boxes", "scores", "prior_idx", "count")})
+
+        res["gather_sec"] = time_region(one_gather, steps, warmup, barrier)
+        g = gathered["g"]
+        res["gather_bytes"] = int(sum(v.numel() * v.element_size() for v in g.values()))
+        res["gather_rows"] = int(g["count"].shape[0])
     if want_e2e:
         hsets = 2
         dsteps_ = []
@@ -467,12 +587,6 @@ def main():
     cfg["seed"] = cfg["seed"] + 7919 * rank          # every rank owns different images
     d = synth.make_train_inputs(**cfg)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    tr = bench_train(d, args.steps, args.warmup, world, barrier, peer)
-    clocks = sampler.stop() if rank == 0 else None
-
     def max_over_ranks(x):
         if world == 1:
             return x
@@ -480,9 +594,53 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sec = max_over_ranks(tr["sec"])
+    def per_rank(x):
+        """min / median / max over ranks of a per-rank time (separates slowest-image skew from communication)."""
+        if world == 1:
+            return None
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        v = sorted(float(p.item()) for p in parts)
+        return {"min": v[0], "median": v[len(v) // 2], "max": v[-1]}
+
+    def train_object(dd, steps, label, counters_key, note, want_e2e):
+        """value / roofline (/ e2e) of the training step on batch `dd` (per GPU)."""
+        tt = bench_train(dd, steps, 3, world, barrier, peer, want_e2e=want_e2e, pdl=True)
+        ts = bench_train(dd, steps, 3, world, barrier, peer, want_e2e=False, pdl=False)
+        sec, ssec = max_over_ranks(tt["sec"]), max_over_ranks(ts["sec"])
+        Bq, Pq = dd["B"], dd["P"]
+        k_s = ssec / steps                                      # one serialized back-to-back launch
+        nb = train_bytes_per_image(Pq, dd["M"], float(dd["num_gt"].mean())) * Bq
+        ach = nb / k_s / 1e9
+        o = {"workload": label, "value": world * Bq * steps / sec, "unit": "images/s", "ms_per_step": 1e3 * sec / steps,
+             "steps": steps, "batch_per_gpu": Bq, "global_batch": Bq * world,
+             "serialized_ms_per_step": 1e3 * k_s,
+             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                          "kernel_ms": 1e3 * k_s, "bytes_per_launch": nb,
+                          "traffic": (counters_from_profiles(counters_key) or {}).get("dram_bytes_per_launch"),
+                          "note": note},
+             "issue_roofline": issue_roofline(counters_key, k_s, (clocks or {}).get("sm_mhz") if clocks else None)}
+        if want_e2e:
+            e2 = max_over_ranks(tt["e2e_sec"])
+            o["e2e"] = {"value": world * Bq * steps / e2, "unit": "images/s", "h2d_bytes_per_step": tt["h2d"],
+                        "d2h_bytes_per_step": tt["d2h"],
+                        "numpy_in_value": world * Bq * steps / max_over_ranks(tt["e2e_numpy_in_sec"]),
+                        "one_in_flight_value": world * Bq * steps / max_over_ranks(tt["e2e_serial_sec"])}
+        return o
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    tr = bench_train(d, args.steps, args.warmup, world, barrier, peer, pdl=True, check_allreduce=True)
+    clocks = sampler.stop() if rank == 0 else None
+    # the same steps WITHOUT programmatic dependent launch: every kernel waits for the previous one to drain
+    # (this per-step time is the kernel's duration for the roofline: one launch, back to back, no overlap)
+    ser = bench_train(d, args.steps, args.warmup, world, barrier, peer, want_e2e=False, pdl=False)
+
+    sec, ssec = max_over_ranks(tr["sec"]), max_over_ranks(ser["sec"])
     e2e_sec = max_over_ranks(tr["e2e_sec"])
-    kernel_ms = max_over_ranks(tr["kernel_ms"])
+    kernel_ms = 1e3 * ssec / args.steps
     B, P, M = d["B"], d["P"], d["M"]
     nbar = float(d["num_gt"].mean())
     bytes_per_launch = train_bytes_per_image(P, M, nbar) * B
@@ -491,31 +649,49 @@ def main():
         "metric": "match+loss images/sec", "value": world * B * args.steps / sec, "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": train_config_dict(d, world, cold="inputs rotate over %d device-resident sets (> 2x L2) so no step "
-                                                    "finds its inputs in L2" % tr["nsets"]),
+        "config": dict(train_config_dict(d, world, cold="inputs rotate over %d device-resident sets (> 2x L2) so no step "
+                                                          "finds its inputs in L2" % tr["nsets"]),
+                       launch="one kernel per step, launched back to back with programmatic dependent launch "
+                              "(MBX_FLAG_PDL): step k+1's load / logs / assignment solve start while step k's "
+                              "epilogue, last-CTA reduction and completion are still in flight; every write of "
+                              "step k+1 (gradients, losses, workspace) waits for step k (griddepcontrol.wait). "
+                              "All K steps do all their work inside the timed region; the 'serialized' object is "
+                              "the same loop without the overlap"),
+        "serialized": {"value": world * B * args.steps / ssec, "unit": "images/s", "ms_per_step": kernel_ms,
+                       "per_rank_sec": per_rank(ser["sec"])},
+        "per_rank_sec": per_rank(tr["sec"]),
         "e2e": {"value": world * B * args.steps / e2e_sec, "unit": "images/s",
                 "h2d_bytes_per_step": tr["h2d"], "d2h_bytes_per_step": tr["d2h"],
-                "how": "MultiboxLossStep.step_pinned(use_graph=True, host_results=True, zero_copy=True): the step's "
-                       "inputs sit in one packed PINNED host buffer; one CUDA-graph launch = 1 kernel that streams "
-                       "them over PCIe itself (read-once 16-byte loads from the mapped buffer: the host->device "
-                       "transfer happens inside the kernel, h2d_bytes_per_step bytes every step), solves, and "
-                       "stores the 64-byte loss/status block straight into mapped pinned host memory (with the loss "
-                       "all-reduce fused in when N > 1); the host polls the launch sequence word and checks the "
-                       "status, every step; gradients stay on the device for the backward pass; wall clock.  "
-                       "Measured alternatives (profiles/e2e_modes.py): H2D copy node + D2H copy + stream sync "
-                       "45.7 us, H2D copy node + polled host results 35.3 us, this mode 32.4 us per step"},
+                "numpy_in_value": world * B * args.steps / max_over_ranks(tr["e2e_numpy_in_sec"]),
+                "one_in_flight_value": world * B * args.steps / max_over_ranks(tr["e2e_serial_sec"]),
+                "how": "MultiboxLossStep(host_results=True, zero_copy=True, pdl=True), TWO steps in flight "
+                       "(submit_pinned / wait on rotating step objects): each step's inputs sit in one packed PINNED "
+                       "host buffer (already staged there: 'value'; np.copyto of the caller's numpy arrays into it "
+                       "inside the timed loop: 'numpy_in_value'); ONE kernel per step streams them over PCIe itself "
+                       "(read-once 16-byte loads from the mapped buffer: the host->device transfer happens inside the "
+                       "kernel, h2d_bytes_per_step bytes every step), solves, and stores the 64-byte loss/status block "
+                       "straight into mapped pinned host memory (loss all-reduce fused in when N > 1); the host submits "
+                       "step k+1, then polls step k's launch sequence word and checks its status, every step; gradients "
+                       "stay on the device for the backward pass; wall clock.  'one_in_flight_value' = submit, poll, "
+                       "next (CUDA graph of the one kernel; the round-1 mode)"},
         "gpu_launches": tr["launches_per_step"] * args.steps,
         "collective": ("loss SUM all-reduce fused into the kernel (NVLink peer stores + system-scope arrival "
                        "counters, 4-deep slot ring); step k posts its sums and completes step k-1's reduction, the "
-                       "last step is flushed after the timed region; no NCCL call per step") if world > 1 else None,
-        "last_losses": {"local": tr.get("last"), "global": tr.get("last_global")},
-        "roofline": {"bound": "hbm", "kernel": "mbx_match_loss_kernel", "achieved": achieved, "peak": peak,
+                       "last step is flushed after the timed region; no NCCL call per step; allreduce_check = the "
+                       "fused global sums of the last step against an NCCL all-reduce of the ranks' local fp64 sums"
+                       ) if world > 1 else None,
+        "allreduce_check": tr.get("allreduce_check"),
+        "last_losses": {"local": tr.get("last"), "global": tr.get("last_global"), "pipelined_local": tr.get("last_pipe")},
+        "roofline": {"bound": "hbm", "kernel": "mbx_match_loss_reg_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "peak_kind": "of " + peak_kind,
                      "bytes_per_launch": bytes_per_launch, "kernel_ms": kernel_ms,
-                     "traffic": traffic_from_profiles("mbx_match_loss_kernel"),
+                     "kernel_ms_how": "per-step time of the serialized back-to-back region (one launch per step, "
+                                      "no overlap): an upper bound of the kernel's duration",
+                     "traffic": (counters_from_profiles("cfg2") or {}).get("dram_bytes_per_launch"),
                      "note": "launch/latency-bound at this batch: %d CTAs on 148 SMs, %.2f MB per launch; the "
-                             "solver is bound by dependent shared-memory scans, not HBM (SURVEY.md 8d)"
-                             % (B, bytes_per_launch / 1e6)},
+                             "solver is bound by dependent shared-memory scans and issue slots, not HBM "
+                             "(SURVEY.md 8d)" % (B, bytes_per_launch / 1e6)},
+        "issue_roofline": issue_roofline("cfg2", kernel_ms * 1e-3, (clocks or {}).get("sm_mhz") if clocks else None),
         "clocks": clocks,
     }
     if world > 1:
@@ -523,63 +699,86 @@ def main():
 
     if not args.no_extras:
         # ---- secondary: detect path, BASELINE configs[2]
+        def detect_object(q, dsteps, label, counters_key, want_e2e=True):
+            dr = bench_detect(q, dsteps, max(3, min(args.warmup, 5)), barrier, q["nms_iou"], want_e2e=want_e2e,
+                              world=world)
+            dsec = max_over_ranks(dr["sec"])
+            dk = 1e3 * dsec / dsteps
+            dbytes = detect_bytes_per_image(q["P"], q["keep"]) * q["B"]
+            dach = dbytes / (dk * 1e-3) / 1e9
+            o = {"metric": "decode+NMS images/sec", "value": world * q["B"] * dsteps / dsec, "unit": "images/s",
+                 "steps": dsteps, "ms_per_step": dk, "config": {"workload": label},
+                 "roofline": {"bound": "hbm", "kernel": "mbx_detect_kernel", "achieved": dach, "peak": peak,
+                              "unit": "GB/s", "frac": dach / peak, "bytes_per_launch": dbytes, "kernel_ms": dk,
+                              "traffic": (counters_from_profiles(counters_key) or {}).get("dram_bytes_per_launch")},
+                 "issue_roofline": issue_roofline(counters_key, dk * 1e-3, (clocks or {}).get("sm_mhz") if clocks else None)}
+            if want_e2e:
+                de2e = max_over_ranks(dr["e2e_sec"])
+                o["e2e"] = {"value": world * q["B"] * dsteps / de2e, "unit": "images/s",
+                            "h2d_bytes_per_step": dr["h2d"], "d2h_bytes_per_step": dr["d2h"]}
+            if world > 1:
+                gsec = max_over_ranks(dr["gather_sec"])
+                o["with_gather"] = {"value": world * q["B"] * dsteps / gsec, "unit": "images/s",
+                                    "ms_per_step": 1e3 * gsec / dsteps, "gathered_bytes_per_step": dr["gather_bytes"],
+                                    "gathered_images": dr["gather_rows"],
+                                    "how": "kernel + NCCL all-gather of the padded detections (boxes f64, scores, "
+                                           "prior index, count) of all ranks, every step, inside the timed region"}
+            return o
+
         qcfg = dict(synth.DETECT_CONFIGS["cfg3"])
         qcfg["seed"] += 7919 * rank
         q = synth.make_detect_inputs(**qcfg)
         dsteps = max(20, min(args.steps, 100))
-        dr = bench_detect(q, dsteps, args.warmup, barrier, q["nms_iou"])
-        dsec, dk, de2e = max_over_ranks(dr["sec"]), max_over_ranks(dr["kernel_ms"]), max_over_ranks(dr["e2e_sec"])
-        dbytes = detect_bytes_per_image(q["P"], q["keep"]) * q["B"]
-        dach = dbytes / (dk * 1e-3) / 1e9
-        line["detect"] = {
-            "metric": "decode+NMS images/sec", "value": world * q["B"] * dsteps / dsec, "unit": "images/s",
-            "steps": dsteps, "ms_per_step": 1e3 * dsec / dsteps,
-            "config": {"workload": "BASELINE configs[2]: sigmoid outputs -> decode + clip + filter + top-200 + "
-                                   "greedy NMS (IoU 0.5) + convert, batch %d per GPU, P=%d" % (q["B"], q["P"])},
-            "e2e": {"value": world * q["B"] * dsteps / de2e, "unit": "images/s",
-                    "h2d_bytes_per_step": dr["h2d"], "d2h_bytes_per_step": dr["d2h"]},
-            "roofline": {"bound": "hbm", "kernel": "mbx_detect_kernel", "achieved": dach, "peak": peak,
-                         "unit": "GB/s", "frac": dach / peak, "bytes_per_launch": dbytes, "kernel_ms": dk,
-                         "traffic": traffic_from_profiles("mbx_detect_kernel")},
-        }
-        # ---- a configs[4]-shaped per-GPU shard: where the kernel is throughput-bound
+        line["detect"] = detect_object(q, dsteps, "BASELINE configs[2]: sigmoid outputs -> decode + clip + filter + "
+                                       "top-200 + greedy NMS (IoU 0.5) + convert, batch %d per GPU, P=%d"
+                                       % (q["B"], q["P"]), "detect")
+        # ---- BASELINE configs[4], detect leg: K=11 (P=1420), 8192 images over 8 GPUs = 1024 per GPU, NMS 0.5
+        q5cfg = dict(synth.DETECT_CONFIGS["cfg5d"])
+        q5cfg["B"] = 1024
+        q5cfg["seed"] += 7919 * rank
+        q5 = synth.make_detect_inputs(**q5cfg)
+        line["cfg5_detect"] = detect_object(q5, 10, "BASELINE configs[4] detect leg: 11 aspect ratios (P=%d), 1024 images "
+                                            "per GPU (= 8192 over 8 GPUs), top-200 + NMS 0.5" % q5["P"], "detect_cfg5")
+        # ---- a configs[4]-shaped per-GPU shard of the training step: where the kernel is throughput-bound
         tcfg = dict(K=11, B=1024, M=200, dist="uniform", seed=1005 + 7919 * rank, alpha=1000.0)
         td = synth.make_train_inputs(**tcfg)
-        tsteps = 10
-        tt = bench_train(td, tsteps, 3, world, barrier, peer, want_e2e=False)
-        tsec, tk = max_over_ranks(tt["sec"]), max_over_ranks(tt["kernel_ms"])
-        tbytes = train_bytes_per_image(td["P"], 200, float(td["num_gt"].mean())) * 1024
-        tach = tbytes / (tk * 1e-3) / 1e9
+        line["throughput_shape"] = train_object(
+            td, 10, "BASELINE configs[4] shape: 11 aspect ratios (P=1420), MAX_NUM_BBOXES=200, 1024 images per GPU "
+                    "(= 8192 over 8 GPUs)", "big",
+            "assignment solver: n*P cheap cost bounds + a few exact costs per row (fp32 cost + fp64 duals), "
+            "issue/latency-bound, reported against the HBM figure as the contract asks", want_e2e=True)
         evals = float((td["num_gt"].astype(np.float64) * td["P"]).sum())
-        line["throughput_shape"] = {
-            "workload": "BASELINE configs[4] shape: 11 aspect ratios (P=1420), MAX_NUM_BBOXES=200, 1024 images per GPU",
-            "value": world * 1024 * tsteps / tsec, "unit": "images/s", "ms_per_step": 1e3 * tsec / tsteps,
-            "min_cost_evals_per_s": world * evals * tsteps / tsec,
-            "roofline": {"bound": "hbm", "achieved": tach, "peak": peak, "unit": "GB/s", "frac": tach / peak,
-                         "kernel_ms": tk, "bytes_per_launch": tbytes,
-                         "traffic": traffic_from_profiles("mbx_match_loss_kernel_cfg5shape"),
-                         "note": "assignment solver: >= n*P cost evaluations per image (fp32 cost + fp64 duals), "
-                                 "compute/latency-bound, reported against the HBM figure as the contract asks"},
-        }
-        # ---- BASELINE configs[3]: COCO-person-shaped training step (K=7, P=904, M=100), 1024 images per GPU
+        line["throughput_shape"]["cost_entries_per_s"] = line["throughput_shape"]["value"] / 1024.0 * evals
+        # ---- BASELINE configs[3] as written: batch 1024 TOTAL, sharded by image over the N GPUs (strong scaling)
         c4 = dict(synth.TRAIN_CONFIGS["cfg4"])
-        c4["seed"] += 7919 * rank
-        d4 = synth.make_train_inputs(**c4)
-        s4 = 20
-        t4 = bench_train(d4, s4, 3, world, barrier, peer, want_e2e=False)
-        sec4, k4 = max_over_ranks(t4["sec"]), max_over_ranks(t4["kernel_ms"])
-        b4 = train_bytes_per_image(d4["P"], d4["M"], float(d4["num_gt"].mean())) * d4["B"]
-        a4 = b4 / (k4 * 1e-3) / 1e9
-        line["coco_person_shape"] = {
-            "workload": "BASELINE configs[3] shape: 7 aspect ratios (P=904), MAX_NUM_BBOXES=100, COCO-person-like GT "
-                        "counts (mean %.1f), %d images per GPU" % (float(d4["num_gt"].mean()), d4["B"]),
-            "value": world * d4["B"] * s4 / sec4, "unit": "images/s", "ms_per_step": 1e3 * sec4 / s4,
-            "roofline": {"bound": "hbm", "achieved": a4, "peak": peak, "unit": "GB/s", "frac": a4 / peak,
-                         "kernel_ms": k4, "bytes_per_launch": b4,
-                         "traffic": traffic_from_profiles("mbx_match_loss_kernel_cfg4"),
-                         "note": "sparse GT: the step is dominated by the exact fp32 log / cost arithmetic "
-                                 "(~58% issue-slot utilisation in ncu), not by HBM"},
-        }
+        full = synth.make_train_inputs(**c4)
+        lo, hi = (1024 * rank) // world, (1024 * (rank + 1)) // world
+        shard = dict(full)
+        for k in ("locations", "confidences", "logits", "gt", "num_gt"):
+            if k in shard:
+                shard[k] = np.ascontiguousarray(full[k][lo:hi])
+        shard["B"] = hi - lo
+        so = train_object(shard, 20, "BASELINE configs[3]: COCO-person-shaped training step (K=7, P=904, "
+                          "MAX_NUM_BBOXES=100), batch 1024 TOTAL sharded by image over %d GPU(s): %d images per GPU"
+                          % (world, hi - lo), "cfg4" if world == 1 else None,
+                          "strong scaling: the per-GPU shard shrinks with N (128 images per GPU at N=8: the kernel's "
+                          "latency regime)", want_e2e=True)
+        so["scaling"] = "strong"
+        so["value"] = 1024 * 20 / (so["ms_per_step"] * 1e-3 * 20)       # the GLOBAL batch per step time
+        so["global_batch"] = 1024
+        if "e2e" in so:
+            for kk in ("value", "numpy_in_value", "one_in_flight_value"):
+                so["e2e"][kk] = so["e2e"][kk] * 1024.0 / (shard["B"] * world)
+        line["strong_cfg3"] = so
+        # ---- the same shape, 1024 images per GPU (weak)
+        c4w = dict(c4)
+        c4w["seed"] += 7919 * rank
+        d4 = synth.make_train_inputs(**c4w)
+        line["coco_person_shape"] = train_object(
+            d4, 20, "BASELINE configs[3] shape: 7 aspect ratios (P=904), MAX_NUM_BBOXES=100, COCO-person-like GT "
+                    "counts (mean %.1f), %d images per GPU" % (float(d4["num_gt"].mean()), d4["B"]), "cfg4",
+            "sparse GT: the step is dominated by the exact fp32 log arithmetic and per-image fixed costs, not by HBM",
+            want_e2e=False)
         # ---- the data formats either side of the path, configs[3] shape:
         # per-head NHWC inputs (concat + sigmoid fused away) and ragged ground truth, against the
         # un-fused route (torch.cat of the six heads, then the dense entry point)

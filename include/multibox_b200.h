@@ -215,6 +215,27 @@ int mbx_match_loss_allreduce(const float *locations, const float *confidences,
                              const unsigned long long *peer_buffers, int world, int rank,
                              void *stream);
 
+/* Prepared launches.  A plan holds the argument list of mbx_match_loss_allreduce (world = 1, rank = 0,
+ * peer_buffers = NULL: of mbx_match_loss), checked when it is launched exactly as the direct call checks
+ * it; mbx_match_plan_launch(plan, stream) then enqueues one step with a two-argument foreign call.  For
+ * training loops whose step (a few microseconds at batch 32) is shorter than the host's marshalling of
+ * 24 arguments.  The plan is owned by the caller (destroy it; it holds no device resources) and may be
+ * launched any number of times, on any stream, while the pointers it was created with stay valid. */
+typedef struct mbx_match_plan mbx_match_plan;
+int  mbx_match_plan_create(mbx_match_plan **plan,
+                           const float *locations, const float *confidences,
+                           const float *gt_bboxes, const int32_t *num_gt,
+                           const float *priors, int B, int P, int M, float alpha,
+                           unsigned flags,
+                           int32_t *mask, int32_t *matched_gt_idx,
+                           float *stacked_gt, int32_t *n_stacked,
+                           float *d_locations, float *d_confidences,
+                           float *confidences_out, float *results,
+                           void *workspace, size_t workspace_bytes,
+                           const unsigned long long *peer_buffers, int world, int rank);
+int  mbx_match_plan_launch(const mbx_match_plan *plan, void *stream);
+void mbx_match_plan_destroy(mbx_match_plan *plan);
+
 /* ------------------------------------------------------------------------- *
  * Detection post-processing
  * ------------------------------------------------------------------------- */

@@ -35,6 +35,7 @@ RESULT_WORDS = 16
 EXPORTS = ("mbx_version", "mbx_last_error", "mbx_device_info",
            "mbx_match_workspace_bytes", "mbx_match_loss", "mbx_match_loss_ragged", "mbx_match_loss_heads",
            "mbx_allreduce_buffer_bytes", "mbx_match_loss_allreduce", "mbx_allreduce_flush",
+           "mbx_match_plan_create", "mbx_match_plan_launch", "mbx_match_plan_destroy",
            "mbx_detect_workspace_bytes", "mbx_detect", "mbx_detect_heads",
            "mbx_filter_proposals", "mbx_convert_proposals",
            "mbx_debug_nplog", "mbx_debug_cost_matrix", "mbx_debug_sqrt_mismatches")
@@ -112,6 +113,13 @@ def load():
     lib.mbx_allreduce_buffer_bytes.argtypes = []
     lib.mbx_match_loss_allreduce.restype = _c_int
     lib.mbx_match_loss_allreduce.argtypes = lib.mbx_match_loss.argtypes[:-1] + [_c_void_p, _c_int, _c_int, _c_void_p]
+    lib.mbx_match_plan_create.restype = _c_int
+    lib.mbx_match_plan_create.argtypes = [ctypes.POINTER(_c_void_p)] + lib.mbx_match_loss.argtypes[:-1] + \
+        [_c_void_p, _c_int, _c_int]
+    lib.mbx_match_plan_launch.restype = _c_int
+    lib.mbx_match_plan_launch.argtypes = [_c_void_p, _c_void_p]
+    lib.mbx_match_plan_destroy.restype = None
+    lib.mbx_match_plan_destroy.argtypes = [_c_void_p]
     lib.mbx_allreduce_flush.restype = _c_int
     lib.mbx_allreduce_flush.argtypes = [_c_void_p, _c_void_p, _c_size_t, _c_void_p, _c_int, _c_int, _c_void_p]
     lib.mbx_detect_workspace_bytes.restype = _c_size_t

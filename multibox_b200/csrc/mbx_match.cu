@@ -28,6 +28,8 @@
 // Every thread owns the columns j = tid, tid+T, ... so all per-column traffic is
 // conflict-free and needs no barrier; one __syncthreads per Dijkstra step
 // (the block-wide arg-min) and three per augmentation.
+#include <new>
+
 #include "mbx_match.cuh"
 
 namespace mbx {
@@ -769,6 +771,65 @@ extern "C" int mbx_match_loss_allreduce(const float *locations, const float *con
                            mask, matched_gt_idx, stacked_gt, n_stacked, d_locations, d_confidences, confidences_out,
                            results, workspace, workspace_bytes, peer_buffers, world, rank, stream);
 }
+
+// ---- prepared launches ------------------------------------------------------
+// A plan is the argument list of mbx_match_loss_allreduce, validated once and kept in a caller-owned
+// object: launching it costs one foreign call with two arguments (for latency-critical training loops
+// whose steps are shorter than the host's argument marshalling).
+struct mbx_match_plan {
+    const float *locations, *confidences, *gt_bboxes, *priors;
+    const int32_t *num_gt;
+    int B, P, M;
+    float alpha;
+    unsigned flags;
+    int32_t *mask, *matched_gt_idx, *n_stacked;
+    float *stacked_gt, *d_locations, *d_confidences, *confidences_out, *results;
+    void *workspace;
+    size_t workspace_bytes;
+    unsigned long long peers[MBX_MAX_PEERS];
+    int world, rank;
+};
+
+extern "C" int mbx_match_plan_create(mbx_match_plan **plan, const float *locations, const float *confidences,
+                                     const float *gt_bboxes, const int32_t *num_gt, const float *priors, int B, int P,
+                                     int M, float alpha, unsigned flags, int32_t *mask, int32_t *matched_gt_idx,
+                                     float *stacked_gt, int32_t *n_stacked, float *d_locations, float *d_confidences,
+                                     float *confidences_out, float *results, void *workspace, size_t workspace_bytes,
+                                     const unsigned long long *peer_buffers, int world, int rank) {
+    if (!plan) {
+        set_error("mbx_match_plan_create: null plan pointer");
+        return MBX_E_ARG;
+    }
+    *plan = nullptr;
+    if (world < 1 || world > MBX_MAX_PEERS || rank < 0 || rank >= world || (world > 1 && !peer_buffers)) {
+        set_error("mbx_match_plan_create: bad world=%d rank=%d (max %d ranks)", world, rank, MBX_MAX_PEERS);
+        return MBX_E_ARG;
+    }
+    mbx_match_plan *pl = new (std::nothrow) mbx_match_plan{locations, confidences, gt_bboxes, priors, num_gt, B, P, M,
+                                                          alpha, flags, mask, matched_gt_idx, n_stacked, stacked_gt,
+                                                          d_locations, d_confidences, confidences_out, results,
+                                                          workspace, workspace_bytes, {0}, world, rank};
+    if (!pl) {
+        set_error("mbx_match_plan_create: out of host memory");
+        return MBX_E_ARG;
+    }
+    for (int r = 0; r < MBX_MAX_PEERS; ++r) pl->peers[r] = (world > 1 && r < world) ? peer_buffers[r] : 0ull;
+    *plan = pl;
+    return 0;
+}
+
+extern "C" int mbx_match_plan_launch(const mbx_match_plan *pl, void *stream) {
+    if (!pl) {
+        set_error("mbx_match_plan_launch: null plan");
+        return MBX_E_ARG;
+    }
+    return match_loss_impl(nullptr, pl->locations, pl->confidences, pl->gt_bboxes, pl->num_gt, nullptr, pl->priors, pl->B,
+                           pl->P, pl->M, pl->alpha, pl->flags, pl->mask, pl->matched_gt_idx, pl->stacked_gt, pl->n_stacked,
+                           pl->d_locations, pl->d_confidences, pl->confidences_out, pl->results, pl->workspace,
+                           pl->workspace_bytes, pl->world > 1 ? pl->peers : nullptr, pl->world, pl->rank, stream);
+}
+
+extern "C" void mbx_match_plan_destroy(mbx_match_plan *pl) { delete pl; }
 
 int mbx::match_loss_impl(const mbx_heads *heads, const float *locations, const float *confidences,
                                 const float *gt_bboxes, const int32_t *num_gt, const int32_t *gt_row,

@@ -349,7 +349,9 @@ def merge_patches(per_patch, image_index, num_images, nms_iou=0.5, max_detection
     multibox_b200.patches.merge_patches computes.  per_patch = the list postprocess() returns
     (one dict per patch: boxes f64 [c,4] in image coordinates, scores f32 [c]).  Per image: pool the
     detections of its patches in (patch order, rank) order, stable-argsort-then-reverse by score
-    (ties: later candidate first), keep the top max_detections, greedy NMS on the float32 boxes."""
+    (ties: later candidate first), greedy NMS on the float32 boxes over the pooled candidates (the top
+    1024 by score when there are more: the kernel's per-image capacity), then the first max_detections
+    of the kept list."""
     out = []
     for i in range(num_images):
         pats = [b for b in range(len(per_patch)) if image_index[b] == i]
@@ -357,10 +359,11 @@ def merge_patches(per_patch, image_index, num_images, nms_iou=0.5, max_detection
         scores = np.concatenate([per_patch[b]["scores"].reshape(-1) for b in pats] + [np.zeros((0,), np.float32)], 0)
         src = np.concatenate([np.full(per_patch[b]["scores"].reshape(-1).shape[0], b, np.int32) for b in pats] +
                              [np.zeros((0,), np.int32)], 0)
-        order = np.argsort(scores.astype(np.float32), kind="stable")[::-1][:max_detections]
+        order = np.argsort(scores.astype(np.float32), kind="stable")[::-1][:1024]
         boxes, scores, src = boxes[order], scores[order], src[order]
         if nms_iou is not None and len(order):
             keep = greedy_nms(boxes.astype(np.float32), nms_iou)
             boxes, scores, src = boxes[keep], scores[keep], src[keep]
+        boxes, scores, src = boxes[:max_detections], scores[:max_detections], src[:max_detections]
         out.append(dict(boxes=boxes, scores=scores.astype(np.float32), source_patch=src))
     return out

@@ -66,6 +66,32 @@ for deferred in (False, True):
     if rank == 0:
         print("dist_check world=%d big shard (%d images/rank) deferred=%s: %.4f %.4f -> %s"
               % (world, hi - lo, deferred, gl, gc, "OK" if okb else "MISMATCH"))
+# programmatic dependent launch (MBX_FLAG_PDL) + deferred fused all-reduce: 40 back-to-back device-resident
+# steps over three different shards, no host synchronisation in between; the newest step's global sums
+# (flush) must equal the NCCL all-reduce of that step's local sums
+Bp = 32 * world
+sets = []
+for sd in (11, 12, 13):
+    dp = synth.make_train_inputs(K=5, B=Bp, M=20, seed=sd)
+    lo, hi = mdist.shard_range(Bp)
+    sets.append(mdist.shard_batch({k: dp[k] for k in ("locations", "confidences", "gt", "num_gt")}, Bp))
+step = loss.MultiboxLossStep(hi - lo, dp["P"], 20, dp["priors"], dp["alpha"], peer=peer, deferred_allreduce=True,
+                             pdl=True)
+dev_ = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()      # noqa: E731
+launches = [step.prepare(dev_(x["locations"]), dev_(x["confidences"]).view(hi - lo, -1), dev_(x["gt"]), dev_(x["num_gt"]))
+            for x in sets]
+torch.cuda.synchronize()
+dist.barrier()
+for it in range(40):
+    launches[it % 3]()
+gl, gc = step.flush()
+t64 = step.out["results"][4:8].view(torch.float64).clone()
+dist.all_reduce(t64)
+okp = abs(gl - t64[0].item()) <= 1e-12 * abs(gl) and abs(gc - t64[1].item()) <= 1e-12 * abs(gc)
+ok &= okp
+if rank == 0:
+    print("dist_check world=%d PDL + deferred, 40 back-to-back steps: fused %.6f %.6f nccl %.6f %.6f -> %s"
+          % (world, gl, gc, t64[0].item(), t64[1].item(), "OK" if okp else "MISMATCH"))
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.barrier()
