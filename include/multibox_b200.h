@@ -324,6 +324,13 @@ int mbx_debug_nplog(const float *in, float *out, long long n, void *stream);
 int mbx_debug_sqrt_mismatches(unsigned first_bits, unsigned count, unsigned long long *mismatches,
                               void *stream);
 
+/* Adds to *violations (device uint64, caller-zeroed) the number of float32 bit patterns x in
+ * [first_bits, first_bits+count) for which the fast hardware log the kernels feed into the CHEAP cost
+ * bound differs from the exact (numpy-compatible) log by more than the bound's error analysis allows:
+ * |__logf(x) - log_numpy(x)| > 2^-21 + 2^-19 |__logf(x)| (multibox_b200/csrc/mbx_bound.h). */
+int mbx_debug_fastlog_violations(unsigned first_bits, unsigned count, unsigned long long *violations,
+                                 void *stream);
+
 /* The cost matrix of reference loss.py:33-35 for ONE image, as the matching
  * kernel evaluates it on the fly: loc [P,4] absolute boxes, conf [P] (epsilon
  * added), gt [n,4] -> C [P,n] float64 row-major. */

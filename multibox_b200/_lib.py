@@ -38,7 +38,7 @@ EXPORTS = ("mbx_version", "mbx_last_error", "mbx_device_info",
            "mbx_match_plan_create", "mbx_match_plan_launch", "mbx_match_plan_destroy",
            "mbx_detect_workspace_bytes", "mbx_detect", "mbx_detect_heads",
            "mbx_filter_proposals", "mbx_convert_proposals",
-           "mbx_debug_nplog", "mbx_debug_cost_matrix", "mbx_debug_sqrt_mismatches")
+           "mbx_debug_nplog", "mbx_debug_cost_matrix", "mbx_debug_sqrt_mismatches", "mbx_debug_fastlog_violations")
 
 _lib = None
 MAX_HEADS = 8
@@ -145,6 +145,8 @@ def load():
     lib.mbx_debug_nplog.argtypes = [_c_void_p, _c_void_p, ctypes.c_longlong, _c_void_p]
     lib.mbx_debug_sqrt_mismatches.restype = _c_int
     lib.mbx_debug_sqrt_mismatches.argtypes = [_c_uint, _c_uint, _c_void_p, _c_void_p]
+    lib.mbx_debug_fastlog_violations.restype = _c_int
+    lib.mbx_debug_fastlog_violations.argtypes = [_c_uint, _c_uint, _c_void_p, _c_void_p]
     lib.mbx_debug_cost_matrix.restype = _c_int
     lib.mbx_debug_cost_matrix.argtypes = [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_float,
                                           _c_void_p, _c_void_p]

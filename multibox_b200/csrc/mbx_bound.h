@@ -19,9 +19,15 @@
 //   cheap path : |w - w*| <= u (5.1 h |l|^2 + 2.1 T); gp carries 1 rounding, the FMA chain 4:
 //                |a - (c* - G*)| <= u (40.1 h L Gm + 36.8 h L^2 + 6.2 T);  |G - G*| <= u 20.1 h Gm^2
 //   together   : |c - (a + G)| <= u (115.4 h (L+Gm)^2 + 8.3 T) <= u (231 h L^2 + 231 h Gm^2 + 8.3 T)
-// The margins below use 256 / 256 / 16 (>= 10 % head room, which also covers the round-to-nearest
+// The cheap form may be fed an APPROXIMATE log(c): lc' with |lc' - lc| <= 2^-21 + 2^-19 |lc'| (the kernel uses
+// __logf: absolute error <= 2^-21.41 on [0.5, 2], <= 3 ulp elsewhere -- CUDA C++ Programming Guide, checked
+// on every float32 by mbx_debug_fastlog_violations -- against numpy's log, itself within 4 ulp of the true
+// one); w_j then moves by at most that much, which the T term and the constant below absorb
+// (8.3 u T + 2^-19 T + 2^-21 <= 2^-18 T + 2^-20).
+// The margins below use 256 / 256 (>= 10 % head room, which also covers the round-to-nearest
 // arithmetic of the margins themselves) plus 2^-100 absolute for subnormal intermediates:
-//     |c(i,j) - (a(i,j) + G_i)| <= m_j + mg_i,   m_j = 2^-16 |h| L_j^2 + 2^-20 T_j + 2^-100,  mg_i = 2^-16 |h| Gm_i^2
+//     |c(i,j) - (a(i,j) + G_i)| <= m_j + mg_i,   m_j = 2^-16 |h| L_j^2 + 2^-18 T_j + 2^-20,  mg_i = 2^-16 |h| Gm_i^2
+// with T_j = |lc'_j| + |l1_j| taken from the values the cheap form was built with.
 // A margin above 2^60 or not finite (non-finite inputs, overflow) becomes +inf: nothing is pruned with it.
 #pragma once
 #include <math.h>
@@ -47,7 +53,7 @@ MBX_BOUND_FN float mbx_bound_w(float l0, float l1_, float l2, float l3, float h,
 
 // per-prior margin from L = max_k |l_k| and T = |lc| + |l1| (or any upper bounds of them)
 MBX_BOUND_FN float mbx_bound_margin_col(float L, float T, float h) {
-    const float m = fmaf(1.52587890625e-05f * fabsf(h), L * L, fmaf(9.5367431640625e-07f, T, 7.888609052210118e-31f));
+    const float m = fmaf(1.52587890625e-05f * fabsf(h), L * L, fmaf(3.814697265625e-06f, T, 9.5367431640625e-07f));
     return mbx_bound_cap(m);
 }
 

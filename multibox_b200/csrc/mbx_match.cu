@@ -620,6 +620,25 @@ __global__ void mbx_debug_sqrt_kernel(unsigned first, unsigned count, unsigned l
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// |__logf(x) - numpy log(x)| against the bound mbx_bound.h assumes for the cheap cost form
+__global__ void mbx_debug_fastlog_kernel(unsigned first, unsigned count, unsigned long long *violations) {
+    unsigned long long bad = 0;
+    for (unsigned long long k = blockIdx.x * 256ull + threadIdx.x; k < count; k += 256ull * gridDim.x) {
+        const float x = __uint_as_float(first + static_cast<unsigned>(k));
+        const float a = __logf(x), b = nplogf(x);
+        bool ok;
+        if (b != b)
+            ok = a != a;
+        else if (b == CUDART_INF_F || b == -CUDART_INF_F)
+            ok = a == b;
+        else
+            ok = fabs(static_cast<double>(a) - static_cast<double>(b)) <=
+                 4.76837158203125e-07 + 1.9073486328125e-06 * fabs(static_cast<double>(a));   // 2^-21 + 2^-19 |a|
+        bad += ok ? 0 : 1;
+    }
+    if (bad) atomicAdd(violations, bad);
+}
+
 __global__ void mbx_debug_cost_kernel(const float *loc, const float *conf, const float *gt, int P, int n,
                                       float alpha, double *C) {
     const float half_alpha = __fdiv_rn(alpha, 2.0f);
@@ -654,6 +673,13 @@ extern "C" int mbx_debug_sqrt_mismatches(unsigned first_bits, unsigned count, un
     if (!mismatches) return MBX_E_ARG;
     mbx_debug_sqrt_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(first_bits, count, mismatches);
     return check_cuda(cudaGetLastError(), "launch mbx_debug_sqrt_kernel");
+}
+
+extern "C" int mbx_debug_fastlog_violations(unsigned first_bits, unsigned count, unsigned long long *violations,
+                                            void *stream) {
+    if (!violations) return MBX_E_ARG;
+    mbx_debug_fastlog_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(first_bits, count, violations);
+    return check_cuda(cudaGetLastError(), "launch mbx_debug_fastlog_kernel");
 }
 
 extern "C" int mbx_debug_cost_matrix(const float *loc, const float *conf, const float *gt, int P, int n,

@@ -38,7 +38,8 @@ int launch_match_reg(const MatchParams &p, int force_warps, int force_cols, cuda
     if (nwarps == 0) {
         // CTA width: enough threads that a thread owns <= 3-4 columns (measured best for both the
         // few-image, latency-bound case and the many-image, throughput-bound case on B200).
-        nwarps = p.P <= 96 ? 1 : (p.P <= 192 ? 2 : (p.P <= 384 ? 4 : (p.P <= 1024 ? 8 : 16)));
+        // (up to 6 columns per thread an 8-warp CTA stays within 128 registers: two images per SM)
+        nwarps = p.P <= 96 ? 1 : (p.P <= 192 ? 2 : (p.P <= 384 ? 4 : (p.P <= 1536 ? 8 : 16)));
     }
     int cols = force_cols ? force_cols : (p.P + nwarps * 32 - 1) / (nwarps * 32);
     while (!force_warps && cols > 8 && nwarps < 16) {

@@ -272,7 +272,7 @@ struct ColState {
 // thread owns few columns; wide per-thread footprints (C >= 5) trade occupancy for registers.
 template <int NWARPS, int C>
 constexpr int min_blocks_per_sm() {
-    const int warps_per_sm = (C == 4) ? 24 : ((C <= 3) ? 16 : ((C <= 6) ? 12 : 8));
+    const int warps_per_sm = (C == 4) ? 24 : ((C <= 6) ? 16 : 8);
     return (NWARPS >= warps_per_sm) ? 1 : warps_per_sm / NWARPS;
 }
 
@@ -369,7 +369,11 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
         const size_t row0 = static_cast<size_t>(b) * P;
         // ---- per-column state in registers
         float4 loc[C];
-        float lc[C], l1[C], cf[C], wq[C];
+        // lca: a FAST approximation of log(c) (2 instructions), good enough for the cheap cost form -- its
+        // error is part of the margin (mbx_bound.h).  The exact numpy log of c (loss.py:21, ~45
+        // instructions) is only needed where an exact cost is evaluated and for the matched priors'
+        // loss term, so it is computed there, on demand: a few columns per row instead of all of them.
+        float lca[C], l1[C], cf[C], wq[C];
         ColState<double, C, RS> cv, spc;     // dual v; shortest path cost of the current search
         ColState<short, C, RS> ptag, arow;   // visit index of the row that set spc; row the column had when scanned
         unsigned vnz = 0u;    // which of this thread's columns have a non-zero dual
@@ -420,27 +424,29 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                     if (p.conf_out) p.conf_out[row0 + j] = cf[c];
                 }
                 const float ce = boundary ? cf[c] : __fadd_rn(cf[c], kEps32);   // loss.py:74
-                lc[c] = n > 0 ? nplogf(ce) : 0.0f;   // loss.py:21 (only ever read for an image that has GT rows)
+                lca[c] = __logf(ce);                                             // (see above; exact: exact_lc())
                 float w = __fsub_rn(1.0f, ce);                                   // loss.py:22-24
                 if (w > 1.0f) w = 1.0f;
                 if (w <= 0.0f) w = kEps32;
                 l1[c] = nplogf(w);                                               // loss.py:25
                 if (n > 0) {
-                    wq[c] = mbx_bound_w(loc[c].x, loc[c].y, loc[c].z, loc[c].w, half_alpha, lc[c], l1[c]);
+                    wq[c] = mbx_bound_w(loc[c].x, loc[c].y, loc[c].z, loc[c].w, half_alpha, lca[c], l1[c]);
                     // (uint order == float order on |x|; inf / NaN patterns come out on top and disable pruning)
                     const unsigned mx = max(max(__float_as_uint(fabsf(loc[c].x)), __float_as_uint(fabsf(loc[c].y))),
                                             max(__float_as_uint(fabsf(loc[c].z)), __float_as_uint(fabsf(loc[c].w))));
                     lmax = max(lmax, mx);
-                    tmax = max(tmax, __float_as_uint(__fadd_rn(fabsf(lc[c]), fabsf(l1[c]))));
+                    tmax = max(tmax, __float_as_uint(__fadd_rn(fabsf(lca[c]), fabsf(l1[c]))));
                 } else {
                     wq[c] = 0.0f;
                 }
             } else {
-                lc[c] = -CUDART_INF_F;   // a column that does not exist costs +inf: never selected
+                lca[c] = 0.0f;           // a column that does not exist is never evaluated (invalid_mask)
                 l1[c] = 0.0f;
                 wq[c] = CUDART_INF_F;
             }
         }
+        // exact log(c) of reference loss.py:21 for a confidence as loaded (bit-equal to numpy's float32 log)
+        auto exact_lc = [&](float cfv) { return nplogf(boundary ? cfv : __fadd_rn(cfv, kEps32)); };
         float m_w = CUDART_INF_F;   // margin of the cheap cost form for the columns of this warp
         if (n > 0) {
             lmax = __reduce_max_sync(0xffffffffu, lmax);
@@ -479,7 +485,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
         // Pass 1 (no barrier, RB*C independent 4-FMA chains per thread): the cheap form of every
         // entry; per-warp minimum of each row -> rowpart.
         if (n > 0) {
-            constexpr int RB = (C <= 3) ? 4 : ((C <= 4) ? 3 : 2);
+            constexpr int RB = (C <= 3) ? 4 : 2;
             for (int i0 = 0; i0 < n; i0 += RB) {
                 float4 gq[RB];
                 float best[RB];
@@ -513,7 +519,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             auto eval_exact = [&](int entry) {
                 const int row = entry >> 3, c = entry & 7;
                 float4 l = loc[0];
-                float lcv = lc[0], l1v = l1[0];
+                float cfv = cf[0], l1v = l1[0];
 #pragma unroll
                 for (int q2 = 1; q2 < C; ++q2) {
                     const bool hit = q2 == c;
@@ -521,10 +527,10 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                     l.y = hit ? loc[q2].y : l.y;
                     l.z = hit ? loc[q2].z : l.z;
                     l.w = hit ? loc[q2].w : l.w;
-                    lcv = hit ? lc[q2] : lcv;
+                    cfv = hit ? cf[q2] : cfv;
                     l1v = hit ? l1[q2] : l1v;
                 }
-                const float c32 = cost32(l, s.gt[row], half_alpha, lcv, l1v);
+                const float c32 = cost32(l, s.gt[row], half_alpha, exact_lc(cfv), l1v);
                 ok = ok && (c32 > -CUDART_INF_F);
                 MBX_COUNT(9, 1);
                 const unsigned long long k32 = ord32(c32);
@@ -722,7 +728,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                             const int c = __ffs(cand) - 1;
                             cand &= cand - 1u;
                             float4 l = loc[0];
-                            float lcv = lc[0], l1v = l1[0];
+                            float cfv = cf[0], l1v = l1[0];
 #pragma unroll
                             for (int q2 = 1; q2 < C; ++q2) {
                                 const bool hit = q2 == c;
@@ -730,10 +736,10 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                                 l.y = hit ? loc[q2].y : l.y;
                                 l.z = hit ? loc[q2].z : l.z;
                                 l.w = hit ? loc[q2].w : l.w;
-                                lcv = hit ? lc[q2] : lcv;
+                                cfv = hit ? cf[q2] : cfv;
                                 l1v = hit ? l1[q2] : l1v;
                             }
-                            const float c32 = cost32(l, g, half_alpha, lcv, l1v);
+                            const float c32 = cost32(l, g, half_alpha, exact_lc(cfv), l1v);
                             ok = ok && (c32 > -CUDART_INF_F);
                             MBX_COUNT(9, 1);
                             const int jc = tid + c * T;
@@ -933,9 +939,18 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             if (p.gt_idx) p.gt_idx[row0 + j] = r;
             n_match += r >= 0;
             const float ce = boundary ? cf[c] : __fadd_rn(cf[c], kEps32);
+            // unmatched prior (almost all of them), unconditionally: -log((1 - c) + eps) and its derivative
+            // (__frcp_rn is the correctly rounded reciprocal: the same bits as the IEEE division 1 / x)
+            const float one_m = __fsub_rn(1.0f, ce);
+            const float arg = __fadd_rn(one_m, kEps32);   // loss.py:101
+            float vcl = one_m;
+            if (vcl > 1.0f) vcl = 1.0f;
+            if (vcl <= 0.0f) vcl = kEps32;
+            float la = l1[c];
+            if (arg != vcl) la = nplogf(arg);             // (only for saturated confidences)
             float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);
-            float dc;
-            if (r >= 0) {
+            float dc = __frcp_rn(arg);
+            if (r >= 0) {                                 // matched: location term, -log(c), their derivatives
                 const float4 g = s.gt[r];
                 const float d0 = __fsub_rn(loc[c].x, g.x), d1 = __fsub_rn(loc[c].y, g.y),
                             d2 = __fsub_rn(loc[c].z, g.z), d3 = __fsub_rn(loc[c].w, g.w);
@@ -945,18 +960,10 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                 acc_sq += static_cast<double>(__fmul_rn(d3, d3));
                 dl = make_float4(__fmul_rn(p.alpha, d0), __fmul_rn(p.alpha, d1), __fmul_rn(p.alpha, d2),
                                  __fmul_rn(p.alpha, d3));
-                acc_conf -= static_cast<double>(lc[c]);
-                dc = __fdiv_rn(-1.0f, ce);
-            } else {
-                const float one_m = __fsub_rn(1.0f, ce);
-                const float arg = __fadd_rn(one_m, kEps32);   // loss.py:101
-                float vcl = one_m;
-                if (vcl > 1.0f) vcl = 1.0f;
-                if (vcl <= 0.0f) vcl = kEps32;
-                const float la = (arg == vcl) ? l1[c] : nplogf(arg);
-                acc_conf -= static_cast<double>(la);
-                dc = __fdiv_rn(1.0f, arg);
+                la = exact_lc(cf[c]);
+                dc = -__frcp_rn(ce);
             }
+            acc_conf -= static_cast<double>(la);
             if (logits) dc = __fmul_rn(dc, __fmul_rn(cf[c], __fsub_rn(1.0f, cf[c])));
             if (nheads > 1) {   // gradients in the per-head layouts too
                 int hh;

@@ -255,8 +255,10 @@ void orc_cost_matrix(const float *loc, const float *conf, const float *gt, int64
  * is reported as +inf. */
 #include "../../multibox_b200/csrc/mbx_bound.h"
 
-double orc_bound_max_ratio(const float *loc, const float *lc, const float *l1, const float *gt, int64_t P,
-                           int64_t n, float alpha, int64_t *n_unbounded)
+/* lc_w: the (possibly approximate) log(c) the cheap form is built with -- the kernels use a fast
+ * hardware log there; lc: the exact numpy log the cost entry uses. */
+double orc_bound_max_ratio(const float *loc, const float *lc, const float *lc_w, const float *l1, const float *gt,
+                           int64_t P, int64_t n, float alpha, int64_t *n_unbounded)
 {
     const float h = alpha / 2.0f;
     double worst = 0.0;
@@ -271,10 +273,10 @@ double orc_bound_max_ratio(const float *loc, const float *lc, const float *l1, c
             float Lx = L;
             for (int k = 0; k < 4; k++)
                 if (!(fabsf(l[k]) <= 3.4028234663852886e38f)) Lx = NAN;
-            const float T = fabsf(lc[p]) + fabsf(l1[p]);
+            const float T = fabsf(lc_w[p]) + fabsf(l1[p]);
             const float m = mbx_bound_margin_col(Lx, T, h);
             if (isinf(m) || isinf(mg)) { unb++; continue; }
-            const float w = mbx_bound_w(l[0], l[1], l[2], l[3], h, lc[p], l1[p]);
+            const float w = mbx_bound_w(l[0], l[1], l[2], l[3], h, lc_w[p], l1[p]);
             const float a = mbx_bound_a(l[0], l[1], l[2], l[3], gp[0], gp[1], gp[2], gp[3], w);
             const double c = cost_entry(l, g, h, lc[p], l1[p]);
             const double err = fabs(c - ((double)a + (double)G));

@@ -15,15 +15,26 @@ from multibox_b200 import synth
 from oracle import c_oracle
 
 
-def _ratio(loc, lc, l1, gt, alpha):
+def _approx_log(lc, rng=None):
+    """A log(c) as wrong as the kernels' fast log may be: |lc' - lc| = 2^-21 + 2^-20 |lc| (the documented bound
+    of __logf against the true log plus numpy's own 4 ulp), random sign."""
+    lc = np.asarray(lc, np.float32)
+    rng = np.random.default_rng(0) if rng is None else rng
+    sign = rng.choice([-1.0, 1.0], size=lc.shape)
+    with np.errstate(all="ignore"):
+        return (lc.astype(np.float64) + sign * (2.0 ** -21 + 2.0 ** -20 * np.abs(lc.astype(np.float64)))).astype(np.float32)
+
+
+def _ratio(loc, lc, l1, gt, alpha, lc_w=None):
     L = c_oracle.lib()
     L.orc_bound_max_ratio.restype = ctypes.c_double
     loc = np.ascontiguousarray(loc, np.float32)
     lc = np.ascontiguousarray(lc, np.float32)
+    lc_w = np.ascontiguousarray(_approx_log(lc) if lc_w is None else lc_w, np.float32)
     l1 = np.ascontiguousarray(l1, np.float32)
     gt = np.ascontiguousarray(gt, np.float32)
     unb = ctypes.c_int64(0)
-    r = L.orc_bound_max_ratio(c_oracle._p(loc), c_oracle._p(lc), c_oracle._p(l1), c_oracle._p(gt),
+    r = L.orc_bound_max_ratio(c_oracle._p(loc), c_oracle._p(lc), c_oracle._p(lc_w), c_oracle._p(l1), c_oracle._p(gt),
                               ctypes.c_int64(loc.shape[0]), ctypes.c_int64(gt.shape[0]), ctypes.c_float(alpha),
                               ctypes.byref(unb))
     return r, unb.value

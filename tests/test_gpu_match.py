@@ -379,3 +379,16 @@ def test_nplog_exhaustive_on_gpu(cuda_device):
         got = gpu_nplog(x).view(np.uint32)
         want = c_oracle.nplog(x).view(np.uint32)
         assert np.array_equal(got, want), hex(first)
+
+
+def test_fast_log_within_the_bound_on_every_float(cuda_device):
+    """The cheap cost bound is fed the hardware's fast log of the confidence; its error analysis
+    (mbx_bound.h) assumes |__logf(x) - numpy log(x)| <= 2^-21 + 2^-19 |__logf(x)|.  Checked here on EVERY
+    float32 bit pattern (zeros, denormals, negatives, infinities and NaNs included)."""
+    from multibox_b200 import _lib
+    lib = _lib.load()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for first in (0x00000000, 0x40000000, 0x80000000, 0xC0000000):
+        _lib.check(lib.mbx_debug_fastlog_violations(first, 0x40000000, bad.data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream), "fast log check")
+    assert bad.item() == 0
