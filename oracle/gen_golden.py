@@ -16,6 +16,7 @@ Fixtures
   match_cfg1.npz     BASELINE configs[0]: seed-regenerated inputs (sha256 pinned)
   match_cfg2.npz     BASELINE configs[1] inputs, reference mask / stacked GT
   detect_small.npz   detect loop body on B=12 mixed patches (whole / crop / flip)
+  eval_small.npz     eval loop body (eval.py:142-175 executed verbatim) on B=6 images, top-100 rows
   detect_cfg3_head.npz  first 16 images of configs[2] (no NMS: reference has none)
   patches.npz        extract_patches geometry (detect.py:20-72) for six image / crop shapes
 """
@@ -159,6 +160,22 @@ def gen_detect():
     print("detect_cfg3_head.npz rows =", len(ids))
 
 
+def gen_eval():
+    """eval_small.npz: the reference's own eval loop (eval.py:142-175, executed verbatim) on B=6 images,
+    with exact confidence ties; the numpy restatement must reproduce its rows bit for bit."""
+    d = synth.make_detect_inputs(K=5, B=6, keep=100, seed=8)
+    d["confidences"][1, 5:60, 0] = d["confidences"][1, 5, 0]
+    d["confidences"][3, :, 0] = np.float32(0.25)
+    rows = ref_slices.eval_loop_body(d["locations"], d["confidences"], d["priors"], 299, d["image_ids"])
+    mine = np_oracle.eval_topk(d["locations"], d["confidences"], d["priors"], 299, d["image_ids"], k=100)
+    a = np.array([[float(np.asarray(v).reshape(-1)[0]) for v in r] for r in rows], dtype=np.float64)
+    b = np.array(mine, dtype=np.float64)
+    assert a.shape == b.shape == (600, 7) and np.array_equal(a, b)
+    np.savez_compressed(os.path.join(GOLD, "eval_small.npz"), priors=d["priors"], locations=d["locations"],
+                        confidences=d["confidences"], image_ids=d["image_ids"], rows=a)
+    print("eval_small.npz rows =", a.shape[0])
+
+
 PATCH_CASES = [(600, 800, (299, 299), (113, 113)), (299, 299, (299, 299), (113, 113)),
                (480, 640, (185, 185), (69, 69)), (200, 500, (299, 299), (113, 113)),
                (525, 412, (185, 185), (69, 69)), (299, 412, (299, 299), (113, 113))]   # == tests/test_patches.py CASES
@@ -199,6 +216,7 @@ def main():
     gen_priors()
     gen_match()
     gen_detect()
+    gen_eval()
     gen_patches()
 
 

@@ -16,6 +16,9 @@ Slices:
                         integer division at loss.py:16 becomes ``//``
   * detect.py:74-131    filter_proposals / convert_proposals -- verbatim
   * detect.py:20-72     extract_patches (patch geometry; called with an all-zero image) -- verbatim
+  * eval.py:142-175     the per-image loop of eval() (decode, clip, scale, sort, top-100 rows),
+                        executed VERBATIM (dedented) by ``eval_loop_body`` with one shim: the unstable
+                        ``np.argsort(x)`` at eval.py:162 gets ``kind='stable'`` (tie order pinned)
 The inline loop body detect.py:408-436 is not a function; its statement order
 is followed by ``detect_loop_body`` below, calling the verbatim functions, with
 ``np.asscalar`` -> ``.item()`` and ``np.argsort(kind='stable')`` pinned (numpy's
@@ -93,3 +96,26 @@ def detect_loop_body(locs, confs, bbox_priors, patch_offsets, patch_dims,
                 "score": float(filtered_confs[k].item()),
             })
     return detection_results
+
+
+def eval_loop_body(locs, confs, bbox_priors, input_size, image_ids):
+    """Executes reference eval.py:142-175 verbatim (the ``for b in range(cfg.BATCH_SIZE)`` loop up to the
+    ``pred_annotations.append`` of the top-100 rows) in a namespace that provides the names the loop
+    reads.  One shim: ``np.argsort(predicted_confs.ravel())`` -> ``kind='stable'``.  Returns
+    pred_annotations: rows [img_id, x1, y1, w, h, score, 1]."""
+    import textwrap
+    src = _slice("eval.py", 142, 175)
+    shim_from = "np.argsort(predicted_confs.ravel())[::-1]"
+    assert src.count(shim_from) == 1, "reference eval.py:162 changed"
+    src = textwrap.dedent(src.replace(shim_from, "np.argsort(predicted_confs.ravel(), kind='stable')[::-1]"))
+
+    class _Cfg:
+        BATCH_SIZE = int(locs.shape[0])
+        INPUT_SIZE = int(input_size)
+
+    B = int(locs.shape[0])
+    ns = {"np": np, "cfg": _Cfg, "locs": locs, "confs": confs, "bbox_priors": bbox_priors, "image_ids": image_ids,
+          "all_gt_bboxes": np.zeros((B, 1, 4), np.float32), "all_gt_num_bboxes": np.zeros((B,), np.int32),
+          "all_gt_areas": np.zeros((B, 1), np.float32), "pred_annotations": []}
+    exec(compile(src, "ref:eval.py:142-175(+stable)", "exec"), ns)
+    return ns["pred_annotations"]

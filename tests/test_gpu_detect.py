@@ -154,6 +154,41 @@ def test_eval_topk_rows(cuda_device):
     assert np.array_equal(np.array(rows0, dtype=np.float64), np.array(rows1, dtype=np.float64))
 
 
+def test_eval_small_golden(cuda_device, golden_dir):
+    """detect.eval_topk against the rows the reference's own eval loop (eval.py:142-175, executed
+    verbatim by oracle/gen_golden.py) produced -- exact ties included."""
+    g = np.load(os.path.join(golden_dir, "eval_small.npz"))
+    rows = detect.eval_topk(dev(g["locations"]), dev(g["confidences"]), dev(g["priors"]), 299, g["image_ids"], k=100)
+    assert np.array_equal(np.array(rows, dtype=np.float64), g["rows"])
+
+
+def test_full_size_config2_with_nms_every_image(cuda_device):
+    """BASELINE configs[2] as stated (K=5, B=256, keep 200, NMS IoU 0.5): every image, exact comparison
+    with the oracle (kept prior indices, scores, float32 and float64 boxes)."""
+    cfg = dict(synth.DETECT_CONFIGS["cfg3"])
+    nms = cfg.pop("nms_iou")
+    d = synth.make_detect_inputs(**cfg)
+    assert d["B"] == 256
+    post = np_oracle.postprocess(d["locations"], d["confidences"], d["priors"], d["restrictions"],
+                                 d["max_to_keep"], d["offsets"], d["patch_dims"], d["image_dims"],
+                                 d["is_flipped"], nms_iou=nms)
+    _compare(_run(d, nms_iou=nms), post)
+
+
+def test_full_size_config4_detect_leg(cuda_device):
+    """BASELINE configs[4] detect leg (K=11, P=1420, keep 200, NMS IoU 0.5): 256 images of a per-GPU
+    shard, every one compared exactly with the oracle."""
+    cfg = dict(synth.DETECT_CONFIGS["cfg5d"])
+    nms = cfg.pop("nms_iou")
+    cfg["B"] = 256
+    d = synth.make_detect_inputs(**cfg)
+    assert d["P"] == 1420
+    post = np_oracle.postprocess(d["locations"], d["confidences"], d["priors"], d["restrictions"],
+                                 d["max_to_keep"], d["offsets"], d["patch_dims"], d["image_dims"],
+                                 d["is_flipped"], nms_iou=nms)
+    _compare(_run(d, nms_iou=nms), post)
+
+
 def test_full_size_properties(cuda_device):
     """BASELINE configs[2] at full size (B=256): sortedness, bounds, idempotence."""
     cfg = dict(synth.DETECT_CONFIGS["cfg3"])

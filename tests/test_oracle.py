@@ -245,6 +245,21 @@ def test_eval_topk_shape():
     assert all(sc[i] >= sc[i + 1] for i in range(99))
 
 
+def test_eval_small_golden(golden_dir):
+    """eval_small.npz was written by executing reference eval.py:142-175 VERBATIM (oracle/ref_slices.py
+    eval_loop_body); the numpy restatement must reproduce its rows bit for bit -- and, where the
+    reference checkout is present, so must a fresh execution of the slice."""
+    import os
+    g = np.load(os.path.join(golden_dir, "eval_small.npz"))
+    rows = np_oracle.eval_topk(g["locations"], g["confidences"], g["priors"], 299, g["image_ids"], k=100)
+    assert np.array_equal(np.array(rows, dtype=np.float64), g["rows"])
+    from oracle import ref_slices
+    if ref_slices.available():
+        fresh = ref_slices.eval_loop_body(g["locations"], g["confidences"], g["priors"], 299, g["image_ids"])
+        a = np.array([[float(np.asarray(v).reshape(-1)[0]) for v in r] for r in fresh], dtype=np.float64)
+        assert np.array_equal(a, g["rows"])
+
+
 def test_loss_graph_vs_torch_autograd():
     """Independent check of the oracle's restatement of the TF graph part (loss.py:67-74,88-101) and
     of the hand-derived gradients: the same statements written with torch CPU
