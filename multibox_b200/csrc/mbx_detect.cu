@@ -136,8 +136,8 @@ __host__ __device__ inline size_t dcarve(DSmem *s, unsigned char *base, int P, i
     size_t o_tc = take(sizeof(uint32_t) * 32, 4);                      // remw[w]: boxes of chunk w removed by earlier chunks
     size_t o_kw = take(sizeof(uint32_t) * 32, 4);
     size_t o_kp = take(sizeof(int) * 33, 4);
-    size_t o_kl = take(sizeof(int) * 32, 4);
-    size_t o_cnt = take(sizeof(int) * 4, 4);
+    size_t o_kl = take(sizeof(int) * 64, 4);       // kept rows of a chunk, double buffered
+    size_t o_cnt = take(sizeof(int) * 8, 4);
     if (s) {
         s->priors = reinterpret_cast<float4 *>(base + o_pri);
         s->box = reinterpret_cast<float4 *>(base + o_box);
@@ -259,6 +259,13 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
         bulk_copy_g2s(s.priors, p.priors, static_cast<uint32_t>(sizeof(float4) * P), s.bar);
     }
     bool priors_ready = !has_priors;
+    // Programmatic dependent launch (MBX_FLAG_PDL, see include/multibox_b200.h): this grid may start while
+    // the preceding kernel of the stream (the previous detect step) is still running; everything it shares
+    // with that kernel -- the output tensors -- is only written after griddepcontrol.wait.  Load, decode,
+    // sort and NMS of step k+1 overlap the store phase and the completion of step k.
+    const bool pdl = (p.flags & MBX_FLAG_PDL) != 0;
+    bool dep_done = !pdl;
+    if (pdl) asm volatile("griddepcontrol.launch_dependents;");
 #ifdef MBX_PHASE_TIMING
     long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long t_last = clock64();
@@ -468,112 +475,130 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
             __syncthreads();
             MBX_DT(2);   // diagonal triangles
             unsigned keptw = 0u;   // warp 0, lane c: kept mask of chunk c
-            for (int c = 0; c < W; ++c) {
-                // ---- serial resolve of chunk c by warp 0: 32 shuffles + a 32-step register chain
-                if (warp == 0) {
-                    const unsigned d = s.diag[(c << 5) + lane];
-                    const int left = kk - (c << 5);
-                    const unsigned valid = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
-                    unsigned removed = s.remw[c] | ~valid;
+            // serial resolve of chunk c by warp 0: 32 shuffles + a 32-step register chain; the kept rows go to
+            // klist[buf] / cnt[4 + buf] (double buffered: the other warps may still be reading chunk c-1's list)
+            auto resolve = [&](int c, int buf) {
+                const unsigned d = s.diag[(c << 5) + lane];
+                const int left = kk - (c << 5);
+                const unsigned valid = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+                unsigned removed = s.remw[c] | ~valid;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const unsigned di = __shfl_sync(0xffffffffu, d, i);   // whom box i suppresses (bits > i)
-                        // removed |= (bit i of removed clear) ? di : 0 -- as test-to-predicate + predicated OR:
-                        // two dependent instructions per step on the 32-step chain instead of three
-                        asm("{\n"
-                            ".reg .pred p;\n"
-                            ".reg .b32 t;\n"
-                            "and.b32 t, %0, %2;\n"
-                            "setp.eq.u32 p, t, 0;\n"
-                            "@p or.b32 %0, %0, %1;\n"
-                            "}\n"
-                            : "+r"(removed)
-                            : "r"(di), "r"(1u << i));
-                    }
-                    const unsigned kept = ~removed;
-                    if (lane == c) keptw = kept;
-                    const int nk = __popc(kept);
-                    // klist[l] = row of the l-th kept box of the chunk
-                    s.klist[lane] = lane < nk ? (c << 5) + static_cast<int>(__fns(kept, 0, lane + 1)) : -1;
-                    if (lane == 0) s.cnt[3] = nk;
+                for (int i = 0; i < 32; ++i) {
+                    const unsigned di = __shfl_sync(0xffffffffu, d, i);   // whom box i suppresses (bits > i)
+                    // removed |= (bit i of removed clear) ? di : 0 -- as test-to-predicate + predicated OR:
+                    // two dependent instructions per step on the 32-step chain instead of three
+                    asm("{\n"
+                        ".reg .pred p;\n"
+                        ".reg .b32 t;\n"
+                        "and.b32 t, %0, %2;\n"
+                        "setp.eq.u32 p, t, 0;\n"
+                        "@p or.b32 %0, %0, %1;\n"
+                        "}\n"
+                        : "+r"(removed)
+                        : "r"(di), "r"(1u << i));
                 }
-                MBX_DT(5);   // (timing builds) serial resolve
-                const int nwords = W - 1 - c;
-                if (nwords == 0) break;
-                __syncthreads();
-                MBX_DT(6);   // (timing builds) wait for the resolve
-                // ---- the kept boxes of chunk c against the later chunks.  A lane owns NC boxes (one in
-                // each of NC later chunks: the row broadcast and its bookkeeping are shared by NC
-                // decisions); the warps split the work by (group of NC chunks, slice of the kept rows)
-                // and OR one ballot per chunk into remw[].
-                const int nkept = s.cnt[3];
-                const int myrow = s.klist[lane];
-                auto cross = [&](auto nc_tag) {
-                    constexpr int NC = decltype(nc_tag)::value;
-                    const int CG = (nwords + NC - 1) / NC;
-                    const int RS = CG >= NWARPS ? 1 : NWARPS / CG;
-                    for (int gg = warp; gg < CG * RS; gg += NWARPS) {
-                        const int g = gg % CG, r = gg / CG;
-                        float4 bj[NC];
-                        float aj[NC];
-                        bool jvalid[NC], dead[NC];
-                        bool any_near = false;
+                const unsigned kept = ~removed;
+                if (lane == c) keptw = kept;
+                const int nk = __popc(kept);
+                // klist[l] = row of the l-th kept box of the chunk
+                s.klist[buf * 32 + lane] = lane < nk ? (c << 5) + static_cast<int>(__fns(kept, 0, lane + 1)) : -1;
+                if (lane == 0) s.cnt[4 + buf] = nk;
+            };
+            // The kept boxes of chunk c (list `buf`) against the target chunks w0 .. w0+nw-1, by the warps
+            // wid = 0 .. nwp-1.  A lane owns NC boxes (one in each of NC target chunks: the row broadcast and
+            // its bookkeeping are shared by NC decisions); the warps split the work by (group of NC chunks,
+            // slice of the kept rows) and OR one ballot per chunk into remw[].
+            auto cross = [&](auto nc_tag, int w0, int nw, int wid, int nwp, int buf) {
+                constexpr int NC = decltype(nc_tag)::value;
+                const int nkept = s.cnt[4 + buf];
+                const int myrow = s.klist[buf * 32 + lane];
+                const int CG = (nw + NC - 1) / NC;
+                const int RS = CG >= nwp ? 1 : nwp / CG;
+                for (int gg = wid; gg < CG * RS; gg += nwp) {
+                    const int g = gg % CG, r = gg / CG;
+                    float4 bj[NC];
+                    float aj[NC];
+                    bool jvalid[NC], dead[NC];
+                    bool any_near = false;
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) {
+                        const int w = w0 + g * NC + k;
+                        const int jj = (w << 5) + lane;
+                        jvalid[k] = (g * NC + k) < nw && jj < kk;
+                        bj[k] = s.sbox[jvalid[k] ? jj : 0];
+                        aj[k] = s.sarea[jvalid[k] ? jj : 0];
+                        dead[k] = false;
+                        any_near = any_near || (!thr_ok && jvalid[k]);
+                    }
+                    for (int o = r; o < nkept; o += 2 * RS) {
+                        const int i0 = __shfl_sync(0xffffffffu, myrow, o);
+                        const bool on1 = o + RS < nkept;
+                        const int i1 = on1 ? __shfl_sync(0xffffffffu, myrow, (o + RS) & 31) : i0;
+                        const float4 b0 = s.sbox[i0], b1 = s.sbox[i1];
+                        const float a0 = s.sarea[i0], a1 = s.sarea[i1];
 #pragma unroll
                         for (int k = 0; k < NC; ++k) {
-                            const int w = c + 1 + g * NC + k;
-                            const int jj = (w << 5) + lane;
-                            jvalid[k] = w < W && jj < kk;
-                            bj[k] = s.sbox[jvalid[k] ? jj : 0];
-                            aj[k] = s.sarea[jvalid[k] ? jj : 0];
-                            dead[k] = false;
-                            any_near = any_near || (!thr_ok && jvalid[k]);
+                            bool n0, n1;
+                            const bool s0 = iou_fast(b0, a0, bj[k], aj[k], p.nms_iou, n0);
+                            const bool s1 = iou_fast(b1, a1, bj[k], aj[k], p.nms_iou, n1);
+                            dead[k] = dead[k] || s0 || s1;      // (i1 == i0 when the second row is off)
+                            any_near = any_near || ((n0 || n1) && jvalid[k]);
                         }
-                        for (int o = r; o < nkept; o += 2 * RS) {
-                            const int i0 = __shfl_sync(0xffffffffu, myrow, o);
-                            const bool on1 = o + RS < nkept;
-                            const int i1 = on1 ? __shfl_sync(0xffffffffu, myrow, (o + RS) & 31) : i0;
-                            const float4 b0 = s.sbox[i0], b1 = s.sbox[i1];
-                            const float a0 = s.sarea[i0], a1 = s.sarea[i1];
+                    }
+                    if (__any_sync(0xffffffffu, any_near)) {   // rare: redo my rows with the IEEE division
+                        for (int k = 0; k < NC; ++k) dead[k] = false;
+                        for (int o = r; o < nkept; o += RS) {
+                            const int i = __shfl_sync(0xffffffffu, myrow, o);
 #pragma unroll
                             for (int k = 0; k < NC; ++k) {
-                                bool n0, n1;
-                                const bool s0 = iou_fast(b0, a0, bj[k], aj[k], p.nms_iou, n0);
-                                const bool s1 = iou_fast(b1, a1, bj[k], aj[k], p.nms_iou, n1);
-                                dead[k] = dead[k] || s0 || s1;      // (i1 == i0 when the second row is off)
-                                any_near = any_near || ((n0 || n1) && jvalid[k]);
+                                bool nr;
+                                bool sp = iou_fast(s.sbox[i], s.sarea[i], bj[k], aj[k], p.nms_iou, nr);
+                                if (nr || !thr_ok) sp = iou_exact(s.sbox[i], s.sarea[i], bj[k], aj[k], p.nms_iou);
+                                dead[k] = dead[k] || sp;
                             }
-                        }
-                        if (__any_sync(0xffffffffu, any_near)) {   // rare: redo my rows with the IEEE division
-                            for (int k = 0; k < NC; ++k) dead[k] = false;
-                            for (int o = r; o < nkept; o += RS) {
-                                const int i = __shfl_sync(0xffffffffu, myrow, o);
-#pragma unroll
-                                for (int k = 0; k < NC; ++k) {
-                                    bool nr;
-                                    bool sp = iou_fast(s.sbox[i], s.sarea[i], bj[k], aj[k], p.nms_iou, nr);
-                                    if (nr || !thr_ok) sp = iou_exact(s.sbox[i], s.sarea[i], bj[k], aj[k], p.nms_iou);
-                                    dead[k] = dead[k] || sp;
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < NC; ++k) {
-                            const unsigned m = __ballot_sync(0xffffffffu, dead[k] && jvalid[k]);
-                            if (lane == 0 && m) atomicOr(&s.remw[c + 1 + g * NC + k], m);
                         }
                     }
-                };
-                // boxes per lane: the split that leaves the fewest empty (chunk, lane) slots
-                if (nwords >= 7 || nwords == 4)
-                    cross(std::integral_constant<int, 4>{});
-                else if (nwords >= 3)       // 6 = 3+3, 5 = 3+2, 3
-                    cross(std::integral_constant<int, 3>{});
-                else if (nwords == 2)
-                    cross(std::integral_constant<int, 2>{});
-                else
-                    cross(std::integral_constant<int, 1>{});
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) {
+                        const unsigned m = __ballot_sync(0xffffffffu, dead[k] && jvalid[k]);
+                        if (lane == 0 && m) atomicOr(&s.remw[w0 + g * NC + k], m);
+                    }
+                }
+            };
+            // boxes per lane: the split that leaves the fewest empty (chunk, lane) slots
+            auto cross_any = [&](int w0, int nw, int wid, int nwp, int buf) {
+                if (nw >= 7 || nw == 4)
+                    cross(std::integral_constant<int, 4>{}, w0, nw, wid, nwp, buf);
+                else if (nw >= 3)       // 6 = 3+3, 5 = 3+2, 3
+                    cross(std::integral_constant<int, 3>{}, w0, nw, wid, nwp, buf);
+                else if (nw == 2)
+                    cross(std::integral_constant<int, 2>{}, w0, nw, wid, nwp, buf);
+                else if (nw == 1)
+                    cross(std::integral_constant<int, 1>{}, w0, nw, wid, nwp, buf);
+            };
+            // Schedule.  Chunk c+1 can be resolved as soon as the kept boxes of chunks <= c have been tested
+            // against IT -- not against the chunks after it.  So per chunk c: (A) every warp tests chunk c's
+            // kept boxes against chunk c+1 only; barrier; (B) warp 0 resolves chunk c+1 (the serial 32-step
+            // chain) WHILE the other warps test chunk c's kept boxes against chunks c+2 ..; barrier.
+            if (warp == 0) resolve(0, 0);
+            MBX_DT(5);   // (timing builds) serial resolve
+            __syncthreads();
+            MBX_DT(6);   // (timing builds) wait for the resolve
+            for (int c = 0; c + 1 < W; ++c) {
+                const int buf = c & 1;
+                cross_any(c + 1, 1, warp, NWARPS, buf);                                   // (A)
                 MBX_DT(7);   // (timing builds) cross-chunk suppression
-                __syncthreads();   // remw[c+1..] complete before the next chunk is resolved
+                __syncthreads();   // remw[c+1] complete
+                MBX_DT(6);
+                if (warp == 0) {                                                          // (B)
+                    resolve(c + 1, buf ^ 1);
+                    MBX_DT(5);
+                } else {
+                    cross_any(c + 2, W - 2 - c, warp - 1, NWARPS - 1, buf);
+                    MBX_DT(7);
+                }
+                __syncthreads();   // list of chunk c+1 and remw[c+2..] (from chunk c) complete
+                MBX_DT(6);
             }
             if (warp == 0) {
                 // exclusive prefix of kept counts per word
@@ -593,6 +618,10 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
             MBX_DT(3);   // chunk-serial resolve + cross-chunk suppression
         }
         // ---- store (convert_proposals in float64)
+        if (!dep_done) {   // first global write of this CTA: the preceding grid must be complete
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            dep_done = true;
+        }
         double sx = 1.0, sy = 1.0, ox = 0.0, oy = 0.0;
         int flip = 0;
         if (p.image_dims) {
@@ -687,6 +716,7 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_detect_kernel(const DetectPar
         __syncthreads();   // shared state is reused by the next image
         MBX_DT(4);   // store
     }
+    if (!dep_done) asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef MBX_PHASE_TIMING
     if (lane == 0 && p.out_scores) {
         long long *dbg = reinterpret_cast<long long *>(p.out_scores) + (static_cast<size_t>(blockIdx.x) * NWARPS + warp) * 8;
@@ -700,6 +730,14 @@ static int launch_detect(const DetectParams &p, size_t smem, cudaStream_t st) {
     auto kern = mbx_detect_kernel<NWARPS>;
     static thread_local size_t configured = 0;
     static thread_local int occ = 0;
+    static thread_local int cached_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {   // function attributes and occupancy are per device
+        configured = 0;
+        occ = 0;
+        cached_dev = dev;
+    }
     if (smem > configured || occ == 0) {
         if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     static_cast<int>(smem)),
@@ -716,8 +754,17 @@ static int launch_detect(const DetectParams &p, size_t smem, cudaStream_t st) {
     }
     int grid = sm_count() * occ;
     if (grid > p.B) grid = p.B;
-    kern<<<grid, NWARPS * 32, smem, st>>>(p);
-    return check_cuda(cudaGetLastError(), "launch mbx_detect_kernel");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NWARPS * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (p.flags & MBX_FLAG_PDL) ? 1 : 0;
+    return check_cuda(cudaLaunchKernelEx(&cfg, kern, p), "launch mbx_detect_kernel");
 }
 
 

@@ -100,7 +100,7 @@ def _check_k_max(k_max):
 
 def postprocess(locs, confs, bbox_priors, restrictions=None, max_to_keep=None, offsets=None,
                 patch_dims=None, image_dims=None, is_flipped=None, nms_iou=None, k_max=None,
-                logits=False, want_patch_boxes=True, warps=0, out=None):
+                logits=False, want_patch_boxes=True, warps=0, out=None, pdl=False):
     """The loop body of reference detect.py:408-436 for a whole batch in one
     kernel launch (decode, clip, filter_proposals, top max_to_keep by confidence
     with numpy's stable-argsort-then-reverse tie order, convert_proposals), plus
@@ -110,7 +110,10 @@ def postprocess(locs, confs, bbox_priors, restrictions=None, max_to_keep=None, o
     max_to_keep [B,1] i32, offsets/patch_dims/image_dims [B,2] i32 (y,x)/(h,w),
     is_flipped [B,1] i32.  Returns a dict of padded device tensors:
     boxes f64 [B,k,4] (image coordinates), patch_boxes f32 [B,k,4], scores f32
-    [B,k], prior_idx i32 [B,k] (-1 padding), count i32 [B].  No sync."""
+    [B,k], prior_idx i32 [B,k] (-1 padding), count i32 [B].  No sync.
+    pdl=True (MBX_FLAG_PDL): the caller promises that the inputs are not produced by the kernel that
+    precedes this call on the stream; consecutive calls then overlap (the next call's load / sort / NMS
+    run while this call's store phase completes), with identical results."""
     lib = _lib.load()
     loc = _f32c(locs, "locs")
     B, P = loc.shape[0], loc.shape[1]
@@ -145,7 +148,7 @@ def postprocess(locs, confs, bbox_priors, restrictions=None, max_to_keep=None, o
     scores = buf("scores", (B, k_max), torch.float32)
     idx = buf("prior_idx", (B, k_max), torch.int32)
     cnt = buf("count", (B,), torch.int32)
-    flags = (_lib.FLAG_LOGITS if logits else 0) | (int(warps) << _lib.FLAG_WARPS_SHIFT)
+    flags = (_lib.FLAG_LOGITS if logits else 0) | (int(warps) << _lib.FLAG_WARPS_SHIFT) | (_lib.FLAG_PDL if pdl else 0)
     with torch.cuda.device(dev):      # the library launches on the CUDA current device
         rc = lib.mbx_detect(_lib.ptr(loc), _lib.ptr(conf), _lib.ptr(pri), _lib.ptr(r), _lib.ptr(mk),
                             _lib.ptr(off), _lib.ptr(pd), _lib.ptr(imd), _lib.ptr(fl),
