@@ -220,7 +220,7 @@ def _cpu_detect_shard(args):
     sub = [q[k][lo:hi] for k in ("locations", "confidences")] + [q["priors"]] + \
         [q[k][lo:hi] for k in ("restrictions", "max_to_keep", "offsets", "patch_dims", "image_dims", "is_flipped")]
     out = np_oracle.postprocess(*sub, nms_iou=q["nms_iou"])
-    return int(np.asarray(out["count"]).sum())
+    return int(sum(m["boxes"].shape[0] for m in out))
 
 
 _REF_Q = None
@@ -334,7 +334,8 @@ def time_region(fn, steps, warmup, barrier):
     return e0.elapsed_time(e1) / 1e3
 
 
-def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True, check_allreduce=False):
+def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True, check_allreduce=False,
+                static_schedule=False):
     """Device-resident steps (value) and host-buffer steps (e2e) of match + loss fwd/bwd on batch `d`."""
     import torch
     from multibox_b200 import loss
@@ -348,7 +349,7 @@ def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True,
     gts = rotated_sets(t["gt"], nsets)
     ngs = rotated_sets(t["num_gt"], nsets)
     step = loss.MultiboxLossStep(B, P, M, d["priors"], d["alpha"], device=dev, peer=peer, deferred_allreduce=True,
-                                 pdl=pdl)
+                                 pdl=pdl, static_schedule=static_schedule)
     # one pre-marshalled launch closure per input set: a step is ONE foreign call + one kernel
     launches = [step.prepare(locs[s], confs[s], gts[s], ngs[s]) for s in range(nsets)]
     torch.cuda.synchronize()

@@ -424,7 +424,11 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                     if (p.conf_out) p.conf_out[row0 + j] = cf[c];
                 }
                 const float ce = boundary ? cf[c] : __fadd_rn(cf[c], kEps32);   // loss.py:74
+#ifdef MBX_EXP_EAGER_LC
+                lca[c] = nplogf(ce);
+#else
                 lca[c] = __logf(ce);                                             // (see above; exact: exact_lc())
+#endif
                 float w = __fsub_rn(1.0f, ce);                                   // loss.py:22-24
                 if (w > 1.0f) w = 1.0f;
                 if (w <= 0.0f) w = kEps32;
@@ -446,7 +450,11 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             }
         }
         // exact log(c) of reference loss.py:21 for a confidence as loaded (bit-equal to numpy's float32 log)
+#ifdef MBX_EXP_INLINE_LOG
         auto exact_lc = [&](float cfv) { return nplogf(boundary ? cfv : __fadd_rn(cfv, kEps32)); };
+#else
+        auto exact_lc = [&](float cfv) { return nplogf_cold(boundary ? cfv : __fadd_rn(cfv, kEps32)); };
+#endif
         float m_w = CUDART_INF_F;   // margin of the cheap cost form for the columns of this warp
         if (n > 0) {
             lmax = __reduce_max_sync(0xffffffffu, lmax);
@@ -947,7 +955,11 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             if (vcl > 1.0f) vcl = 1.0f;
             if (vcl <= 0.0f) vcl = kEps32;
             float la = l1[c];
+#ifdef MBX_EXP_INLINE_LOG
             if (arg != vcl) la = nplogf(arg);             // (only for saturated confidences)
+#else
+            if (arg != vcl) la = nplogf_cold(arg);        // (only for saturated confidences)
+#endif
             float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);
             float dc = __frcp_rn(arg);
             if (r >= 0) {                                 // matched: location term, -log(c), their derivatives
@@ -1092,6 +1104,8 @@ int launch_one(const MatchParams &p, cudaStream_t st) {
                                                     static_cast<int>(smem)),
                                "cudaFuncSetAttribute(match_reg)"))
             return e;
+        // (the whole L1/shared array as shared memory: the kernel streams its global data past L1 anyway)
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         info.configured_smem = smem;
         info.occ = 0;
     }

@@ -462,7 +462,7 @@ class MultiboxLossStep:
 
     def __init__(self, B, P, M, priors, alpha, device="cuda", logits=False, want_mask=False,
                  want_stacked=False, warps=0, use_graph=False, peer=None, deferred_allreduce=False,
-                 host_results=False, zero_copy=False, pdl=False):
+                 host_results=False, zero_copy=False, pdl=False, static_schedule=False):
         self.B, self.P, self.M, self.alpha = B, P, M, float(alpha)
         self.device = torch.device(device)
         if self.device.index is None:
@@ -474,6 +474,11 @@ class MultiboxLossStep:
         # load, logs and solve of step k+1 run while step k finishes -- with identical results.
         if pdl:
             self.flags |= _lib.FLAG_PDL
+        # static_schedule (MBX_FLAG_STATIC): image -> CTA assignment by index instead of the heavy-first
+        # dynamic order when the batch exceeds the resident CTAs: no order kernel in front of the step, which
+        # also lets pdl overlap consecutive steps at such sizes; right for batches of similar images.
+        if static_schedule:
+            self.flags |= _lib.FLAG_STATIC
         self.warps = warps
         self.priors = _f32c(torch.as_tensor(priors).to(self.device), "priors")
         self.want_mask, self.want_stacked = want_mask, want_stacked

@@ -30,7 +30,8 @@ def dev(a):
 
 libs = [(os.path.basename(p), load(p)) for p in sys.argv[1:]]
 for label, cfg in (("configs[1] B=32", dict(K=5, B=32, M=20, seed=1002)), ("B=256", dict(K=5, B=256, M=20, seed=3)),
-                   ("cfg4 B=1024", dict(K=7, B=1024, M=100, dist="coco_person", seed=1004))):
+                   ("cfg4 B=1024", dict(K=7, B=1024, M=100, dist="coco_person", seed=1004)),
+                   ("big K=11 B=1024", dict(K=11, B=1024, M=200, dist="uniform", seed=1005))):
     d = synth.make_train_inputs(**cfg)
     B, P, M = d["B"], d["P"], d["M"]
     nsets = max(2, min(256, (300 << 20) // (B * P * 20)))
@@ -62,8 +63,9 @@ for label, cfg in (("configs[1] B=32", dict(K=5, B=32, M=20, seed=1002)), ("B=25
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            for i in range(200):
+            nrep = 200 if B * P < 1000000 else 20
+            for i in range(nrep):
                 run(20 + i)
             b.record()
             torch.cuda.synchronize()
-            print("%-18s %-26s rep %d: %.2f us per back-to-back launch" % (label, name, rep, a.elapsed_time(b) * 1e3 / 200))
+            print("%-18s %-26s rep %d: %.2f us per back-to-back launch" % (label, name, rep, a.elapsed_time(b) * 1e3 / nrep))
