@@ -131,56 +131,6 @@ __host__ __device__ inline size_t carve(Smem *s, unsigned char *base, int P, int
     return align_up(o, 16);
 }
 
-// Heavy-first processing order for the dynamically scheduled matching kernel: the images beyond
-// the first wave (first..B-1) sorted by DESCENDING GT count (counting sort on 256 buckets; the order inside a bucket is arbitrary --
-// every consumer reads the same array, and the results do not depend on the processing order:
-// per-image partials are reduced in image order).  An image's solve time grows with its GT count,
-// so handing out the heavy images first bounds the tail of the launch by a LIGHT image's time
-// (longest-processing-time-first list scheduling).  One CTA of 1024 threads.
-__global__ void __launch_bounds__(1024) mbx_order_kernel(const int32_t *num_gt, const int32_t *gt_row, int first,
-                                                         int B, int M, int32_t *order) {
-    __shared__ int hist[256], start[256];
-    const int tid = threadIdx.x;
-    const int shift = M < 256 ? 0 : (32 - __clz(M >> 8));   // bucket = n >> shift < 256
-    if (tid < 256) hist[tid] = 0;
-    __syncthreads();
-    for (int b = first + tid; b < B; b += 1024) {
-        int n = image_num_gt(num_gt, gt_row, b);
-        n = n < 0 ? 0 : (n > M ? M : n);
-        atomicAdd(&hist[n >> shift], 1);
-    }
-    __syncthreads();
-    if (tid < 32) {   // start[k] = number of images in buckets above k (lane l owns buckets 255-8l .. 248-8l)
-        int part = 0;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) part += hist[255 - 8 * tid - t];
-        int inc = part;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (tid >= o) inc += u;
-        }
-        int run = inc - part;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            start[255 - 8 * tid - t] = run;
-            run += hist[255 - 8 * tid - t];
-        }
-    }
-    __syncthreads();
-    for (int b = first + tid; b < B; b += 1024) {
-        int n = image_num_gt(num_gt, gt_row, b);
-        n = n < 0 ? 0 : (n > M ? M : n);
-        order[atomicAdd(&start[n >> shift], 1)] = b;
-    }
-}
-
-int launch_order(const int32_t *num_gt, const int32_t *gt_row, int first, int B, int M, int32_t *order,
-                 cudaStream_t st) {
-    mbx_order_kernel<<<1, 1024, 0, st>>>(num_gt, gt_row, first, B, M, order);
-    return check_cuda(cudaGetLastError(), "launch mbx_order_kernel");
-}
-
 // exclusive scan of clamp(num_gt, 0, M) -> offsets[B+1]; one CTA of 1024 threads.
 __global__ void __launch_bounds__(1024) mbx_scan_num_gt_kernel(const int32_t *num_gt, const int32_t *gt_row, int B,
                                                                int M, int32_t *offsets, int32_t *n_stacked) {
@@ -552,7 +502,7 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_kernel(const Match
 }
 
 struct WsLayout {
-    size_t partials, img_matched, offsets, order, ticket, status, ar_seq, queue, total;
+    size_t partials, img_matched, offsets, order, ticket, status, ar_seq, lseq, sched, total;
 };
 static WsLayout ws_layout(int B) {
     WsLayout w;
@@ -563,8 +513,10 @@ static WsLayout ws_layout(int B) {
     o += 8;
     w.ar_seq = o;
     o += 8;
-    w.queue = o;     // dynamic image scheduler: next position of the processing order
+    w.lseq = o;      // launch sequence number published with the results
     o += 8;
+    w.sched = o;     // dynamic image scheduler: two slots {queue counter, order-ready flag}
+    o += 16;
     w.partials = o;
     o += sizeof(double) * 2 * static_cast<size_t>(B);
     w.img_matched = o;
@@ -573,8 +525,8 @@ static WsLayout ws_layout(int B) {
     w.offsets = o;
     o += sizeof(int32_t) * (static_cast<size_t>(B) + 1);
     o = align_up(o, 16);
-    w.order = o;
-    o += sizeof(int32_t) * static_cast<size_t>(B);
+    w.order = o;     // two heavy-first orders (alternating launches)
+    o += sizeof(int32_t) * static_cast<size_t>(B) * 2;
     w.total = align_up(o, 256);
     return w;
 }
@@ -963,8 +915,14 @@ int mbx::match_loss_impl(const mbx_heads *heads, const float *locations, const f
     p.img_matched = reinterpret_cast<int32_t *>(ws + wl.img_matched);
     p.stk_offsets = reinterpret_cast<int32_t *>(ws + wl.offsets);
     p.ticket = reinterpret_cast<unsigned *>(ws + wl.ticket);
-    p.order = reinterpret_cast<int32_t *>(ws + wl.order);
-    p.queue = reinterpret_cast<unsigned *>(ws + wl.queue);
+    p.order_base = reinterpret_cast<int32_t *>(ws + wl.order);
+    p.sched_base = reinterpret_cast<unsigned *>(ws + wl.sched);
+    p.order = p.order_base;
+    p.queue = p.sched_base;
+    p.oready = p.sched_base + 2;
+    p.launch_id = 1u;
+    p.order_first = 0;
+    p.lseq = reinterpret_cast<unsigned *>(ws + wl.lseq);
     p.dynamic = 0;
     p.status = reinterpret_cast<unsigned *>(ws + wl.status);
     // the step counter lives in this rank's own symmetric buffer, next to the arrival counters it

@@ -1,9 +1,19 @@
 // multibox_b200 -- dispatch of the register-resident matching kernel family.  The kernel
 // template lives in mbx_match_reg.cuh; its instantiations are compiled in parallel, one
 // translation unit per CTA width (mbx_match_reg_w*.cu).
+#include <unordered_map>
+
 #include "mbx_match.cuh"
 
 namespace mbx {
+
+unsigned next_launch_id(const void *workspace_key) {
+    static thread_local std::unordered_map<const void *, unsigned> launches;
+    unsigned &c = launches[workspace_key];
+    ++c;
+    if (c == 0u) c = 1u;
+    return c;
+}
 
 template <int NWARPS>
 int launch_cols(const MatchParams &p, int cols, cudaStream_t st);

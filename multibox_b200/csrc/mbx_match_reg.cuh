@@ -356,8 +356,27 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     // Thread 0 issues the claim when an image starts and reads it when the image is done, so the
     // L2 round trip of the atomic is off the critical path.
     const bool dyn = p.dynamic != 0;
+    // The heavy-first order is computed by CTA 0 of this very kernel (no kernel in front of it), published
+    // through a ready flag; the first wave either takes the images 0 .. order_first-1 in index order and
+    // never waits, or (order_first == 0: large, skewed images, where a heavy-first first wave is worth 2 us)
+    // waits for the order like everybody else.
+    __shared__ int sh_sort[512];
+    if (dyn && blockIdx.x == 0) {
+        sort_images_heavy_first<T>(p, p.order_first, sh_sort, sh_sort + 256);
+        __threadfence();
+        if (tid == 0) st_release_gpu(p.oready, p.launch_id);
+    }
+    bool order_seen = !dyn;
     for (int q = is_poster ? p.B : static_cast<int>(blockIdx.x); q < p.B;) {
-        const int b = dyn ? __ldcg(p.order + q) : q;
+        int b = q;
+        if (dyn && q >= p.order_first) {
+            if (!order_seen) {
+                while (ld_acquire_gpu(p.oready) != p.launch_id) {
+                }
+                order_seen = true;
+            }
+            b = __ldcg(p.order + (q - p.order_first));
+        }
         unsigned claim = 0u;
         if (dyn && tid == 0) claim = atomicAdd(p.queue, 1u);
         const float4 *gg;
@@ -1120,11 +1139,17 @@ int launch_one(const MatchParams &p, cudaStream_t st) {
     const bool poster = p.ar_world > 1 && (p.flags & MBX_FLAG_AR_DEFERRED);
     MatchParams pp = p;
     if (p.B > units && !(p.flags & MBX_FLAG_STATIC)) {
-        // more images than resident CTAs: heavy-first order + dynamic scheduling
-        if (int e = launch_order(p.num_gt, p.gt_row, 0, p.B, p.M, p.order, st)) return e;
+        // more images than resident CTAs: heavy-first order (computed by CTA 0 of the kernel) + dynamic
+        // scheduling.  Consecutive launches on one workspace alternate between two scheduler slots.
+        const unsigned id = next_launch_id(p.ticket);   // (one counter per workspace, shared by all instantiations)
+        const unsigned slot = id & 1u;
         pp.dynamic = 1;
+        pp.launch_id = id;
+        pp.order = p.order_base + static_cast<size_t>(slot) * p.B;
+        pp.queue = p.sched_base + slot;
+        pp.oready = p.sched_base + 2 + slot;
+        pp.order_first = (p.M >= 128) ? 0 : units;
     }
-    if (pp.dynamic) pp.flags &= ~MBX_FLAG_PDL;   // (the order kernel right before this one produces an input)
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(units + (poster ? 1 : 0));
     cfg.blockDim = dim3(NWARPS * 32);

@@ -25,7 +25,7 @@ for name, cfg, steps in (("configs[3] shape K=7 B=1024 M=100", dict(synth.TRAIN_
                          ("K=5 B=4096 M=20", dict(K=5, B=4096, M=20, seed=3), 20),
                          ("configs[4] shape K=11 B=1024 M=200", dict(K=11, B=1024, M=200, dist="uniform", seed=1005), 10)):
     d = synth.make_train_inputs(**cfg)
-    for static, pdl in ((False, False), (True, False), (True, True), (False, False), (True, True)):
+    for static, pdl in ((False, False), (False, True), (True, True), (False, False), (False, True)):
         tr = bench.bench_train(d, steps, 5, 1, lambda: None, None, want_e2e=False, pdl=pdl, static_schedule=static)
         print("%-40s static=%d pdl=%d  %.2f us/step  (%.3g img/s)" %
               (name, static, pdl, 1e6 * tr["sec"] / steps, d["B"] * steps / tr["sec"]))

@@ -297,3 +297,41 @@ def test_wrong_current_device_is_handled(cuda_device):
     np.testing.assert_allclose(out["results"][:2].cpu().numpy(), [ref["location_loss"], ref["confidence_loss"]], rtol=RTOL)
     with pytest.raises(ValueError):
         loss.match_loss_raw(t[0], t[1].view(4, -1), t[2].to("cuda:0"), t[3], torch.from_numpy(d["priors"]).to(one), 1000.0)
+
+
+def test_programmatic_dependent_launch_with_dynamic_scheduling(cuda_device):
+    """PDL on batches larger than the resident CTAs: the heavy-first order is computed inside the kernel
+    and consecutive launches alternate between two scheduler slots (order array, queue counter, ready
+    flag), so an early-started step never touches what the previous one still uses.  Back-to-back steps
+    over batches of very different weight must equal the plain (serialised) launches bit for bit."""
+    B, P, M = 700, 646, 20
+    heavy = synth.make_train_inputs(K=5, B=B, M=M, dist="full", seed=15)
+    mixed = synth.make_train_inputs(K=5, B=B, M=M, dist="uniform", seed=16)
+    light = synth.make_train_inputs(K=5, B=B, M=M, dist="uniform", seed=17)
+    light["num_gt"][::2] = 0
+    batches = [heavy, mixed, light]
+    plain = loss.MultiboxLossStep(B, P, M, heavy["priors"], 1000.0)
+    want = []
+    for d in batches:
+        o = plain.step(dev(d["locations"]), dev(d["confidences"]).view(B, P), dev(d["gt"]), dev(d["num_gt"]))
+        torch.cuda.synchronize()
+        want.append((o["results"].cpu().numpy().copy(), o["d_locations"].cpu().numpy().copy(),
+                     o["d_confidences"].cpu().numpy().copy()))
+    ref = np_oracle.add_loss(mixed["locations"], mixed["confidences"], mixed["gt"], mixed["num_gt"], mixed["priors"], 1000.0)
+    np.testing.assert_allclose(want[1][0][:2], [ref["location_loss"], ref["confidence_loss"]], rtol=RTOL)
+    step = loss.MultiboxLossStep(B, P, M, heavy["priors"], 1000.0, pdl=True)
+    launches = [step.prepare(dev(d["locations"]), dev(d["confidences"]).view(B, P), dev(d["gt"]), dev(d["num_gt"]))
+                for d in batches]
+    torch.cuda.synchronize()
+    order = [0, 2, 1, 2, 0, 0, 2, 1, 1, 2] * 5
+    snaps = []
+    for k, w in enumerate(order):
+        launches[w]()
+        if k % 6 == 4 or k == len(order) - 1:
+            snaps.append((w, step.out["results"].clone(), step.out["d_locations"].clone(),
+                          step.out["d_confidences"].clone()))
+    torch.cuda.synchronize()
+    for w, res, dl, dc in snaps:
+        assert np.array_equal(res.cpu().numpy()[:15].view(np.uint32), want[w][0][:15].view(np.uint32)), w
+        assert np.array_equal(dl.cpu().numpy().view(np.uint32), want[w][1].view(np.uint32)), w
+        assert np.array_equal(dc.cpu().numpy().view(np.uint32), want[w][2].view(np.uint32)), w
