@@ -92,6 +92,31 @@ ok &= okp
 if rank == 0:
     print("dist_check world=%d PDL + deferred, 40 back-to-back steps: fused %.6f %.6f nccl %.6f %.6f -> %s"
           % (world, gl, gc, t64[0].item(), t64[1].item(), "OK" if okp else "MISMATCH"))
+# the final detection gather: every rank post-processes its shard of one global batch of patches; the packed
+# all-gather must reproduce, bit for bit and in batch order, what one GPU computes on the whole batch
+from multibox_b200 import detect  # noqa: E402
+Bq = 6 * world + 0
+qd = synth.make_detect_inputs(K=5, B=Bq, keep=50, seed=5, patches=True)
+names = ("locations", "confidences", "restrictions", "max_to_keep", "offsets", "patch_dims", "image_dims", "is_flipped")
+lo, hi = mdist.shard_range(Bq)
+
+
+def run_detect(sl):
+    t = {k: dev_(qd[k][sl]) for k in names}
+    return detect.postprocess(t["locations"], t["confidences"], dev_(qd["priors"]), restrictions=t["restrictions"],
+                              max_to_keep=t["max_to_keep"], offsets=t["offsets"], patch_dims=t["patch_dims"],
+                              image_dims=t["image_dims"], is_flipped=t["is_flipped"], nms_iou=0.5, k_max=50)
+
+
+mine = run_detect(slice(lo, hi))
+glob = mdist.gather_detections({k: mine[k] for k in ("boxes", "scores", "prior_idx", "count")})
+full = run_detect(slice(0, Bq))
+torch.cuda.synchronize()
+okg = all(torch.equal(glob[k], full[k]) for k in ("boxes", "scores", "prior_idx", "count"))
+ok &= okg
+if rank == 0:
+    print("dist_check world=%d detection all-gather (%d patches, packed single NCCL call): %s"
+          % (world, Bq, "OK" if okg else "MISMATCH"))
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.barrier()
