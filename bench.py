@@ -316,22 +316,29 @@ def rotated_sets(t, nsets):
     return [torch.roll(t, shifts=r, dims=0).contiguous() if r else t.clone() for r in range(nsets)]
 
 
+MIN_TIMED_STEPS = 200      # a region shorter than this is repeated (see time_region)
+
+
 def time_region(fn, steps, warmup, barrier):
-    """W untimed steps, then EXACTLY `steps` steps between barrier+synchronize on
-    both sides, timed with CUDA events on the launching (current) stream."""
+    """W untimed steps, then `steps` steps between barrier+synchronize on both sides, timed with CUDA
+    events on the launching (current) stream.  A step of this path lasts 5-40 us, so a region of a few
+    dozen steps would be a sub-millisecond measurement: when `steps` < MIN_TIMED_STEPS the region is
+    repeated back to back (R x `steps` steps inside ONE event pair) and the time of `steps` steps is
+    reported as total / R -- every line states steps and timed_steps."""
     import torch
     for i in range(warmup):
         fn(i)
+    reps = max(1, -(-MIN_TIMED_STEPS // max(1, steps)))
     barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(steps):
+    for i in range(steps * reps):
         fn(warmup + i)
     e1.record()
     torch.cuda.synchronize()
     barrier()
-    return e0.elapsed_time(e1) / 1e3
+    return e0.elapsed_time(e1) / 1e3 / reps
 
 
 def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True, check_allreduce=False,
@@ -401,15 +408,16 @@ def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True,
                 fn(i)
             if drain:
                 drain()
+            reps = max(1, -(-MIN_TIMED_STEPS // max(1, n)))       # (same rule as time_region)
             barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            for i in range(n):
+            for i in range(n * reps):
                 fn(max(warmup, hsets) + i)
             if drain:
                 drain()
             torch.cuda.synchronize()
-            return time.perf_counter() - t0
+            return (time.perf_counter() - t0) / reps
 
         last = {}
         # (a) one step in flight: submit, poll, next (the round-1 mode; CUDA graph of the one kernel)
@@ -417,12 +425,15 @@ def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True,
 
         def e2e_serial(i):
             last["v"] = ser[i % hsets].step_pinned(validate=True)
+            last["i"] = i
 
         res["e2e_serial_sec"] = wall(e2e_serial, steps)
         res["last"] = last["v"]
-        res["last_global"] = ser[(max(warmup, hsets) + steps - 1) % hsets].flush()
-        # (b) TWO steps in flight: step k+1 is submitted (its zero-copy PCIe reads and its solve overlap the
-        # tail of step k: programmatic dependent launch) before the host polls step k's result block
+        res["last_global"] = ser[last["i"] % hsets].flush()
+        # (b) THREE steps in flight (four rotating step objects): steps k+1 .. k+3 are submitted (their
+        # zero-copy PCIe reads and solves overlap the tail of step k: programmatic dependent launch) before the
+        # host polls step k's result block -- a single host-buffer step has ~37 us of latency (launch, PCIe
+        # reads, solve, result write-back), so throughput is that latency divided by the steps in flight
         pipe = make(False, True)
         pend = []
 
@@ -432,7 +443,7 @@ def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True,
                 stage(hs, i % hsets)
             hs.submit_pinned()
             pend.append(hs)
-            if len(pend) > 1:
+            if len(pend) > hsets - 1:         # hsets - 1 = 3 steps in flight
                 last["p"] = pend.pop(0).wait(validate=True)
 
         def drain():
@@ -625,6 +636,7 @@ def main():
                           "traffic": (counters_from_profiles(counters_key) or {}).get("dram_bytes_per_launch"),
                           "note": note},
              "issue_roofline": issue_roofline(counters_key, k_s, (clocks or {}).get("sm_mhz") if clocks else None)}
+        o["roofline"]["frac_at_step_rate"] = nb / (sec / steps) / 1e9 / peak      # with consecutive steps overlapped (PDL)
         if want_e2e:
             e2 = max_over_ranks(tt["e2e_sec"])
             o["e2e"] = {"value": world * Bq * steps / e2, "unit": "images/s", "h2d_bytes_per_step": tt["h2d"],
@@ -652,6 +664,7 @@ def main():
     line = {
         "metric": "match+loss images/sec", "value": world * B * args.steps / sec, "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
+        "timed_steps": args.steps * max(1, -(-MIN_TIMED_STEPS // max(1, args.steps))),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(train_config_dict(d, world, cold="inputs rotate over %d device-resident sets (> 2x L2) so no step "
                                                           "finds its inputs in L2" % tr["nsets"]),
@@ -668,14 +681,14 @@ def main():
                 "h2d_bytes_per_step": tr["h2d"], "d2h_bytes_per_step": tr["d2h"],
                 "numpy_in_value": world * B * args.steps / max_over_ranks(tr["e2e_numpy_in_sec"]),
                 "one_in_flight_value": world * B * args.steps / max_over_ranks(tr["e2e_serial_sec"]),
-                "how": "MultiboxLossStep(host_results=True, zero_copy=True, pdl=True), TWO steps in flight "
-                       "(submit_pinned / wait on rotating step objects): each step's inputs sit in one packed PINNED "
+                "how": "MultiboxLossStep(host_results=True, zero_copy=True, pdl=True), THREE steps in flight "
+                       "(submit_pinned / wait on four rotating step objects): each step's inputs sit in one packed PINNED "
                        "host buffer (already staged there: 'value'; np.copyto of the caller's numpy arrays into it "
                        "inside the timed loop: 'numpy_in_value'); ONE kernel per step streams them over PCIe itself "
                        "(read-once 16-byte loads from the mapped buffer: the host->device transfer happens inside the "
                        "kernel, h2d_bytes_per_step bytes every step), solves, and stores the 64-byte loss/status block "
                        "straight into mapped pinned host memory (loss all-reduce fused in when N > 1); the host submits "
-                       "step k+1, then polls step k's launch sequence word and checks its status, every step; gradients "
+                       "step k+3, then polls step k's launch sequence word and checks its status, every step; gradients "
                        "stay on the device for the backward pass; wall clock.  'one_in_flight_value' = submit, poll, "
                        "next (CUDA graph of the one kernel; the round-1 mode)"},
         "gpu_launches": tr["launches_per_step"] * args.steps,
@@ -691,6 +704,7 @@ def main():
                      "bytes_per_launch": bytes_per_launch, "kernel_ms": kernel_ms,
                      "kernel_ms_how": "per-step time of the serialized back-to-back region (one launch per step, "
                                       "no overlap): an upper bound of the kernel's duration",
+                     "frac_at_step_rate": bytes_per_launch / (sec / args.steps) / 1e9 / peak,
                      "traffic": (counters_from_profiles("cfg2") or {}).get("dram_bytes_per_launch"),
                      "note": "launch/latency-bound at this batch: %d CTAs on 148 SMs, %.2f MB per launch; the "
                              "solver is bound by dependent shared-memory scans and issue slots, not HBM "
