@@ -317,6 +317,7 @@ def rotated_sets(t, nsets):
 
 
 MIN_TIMED_STEPS = 200      # a region shorter than this is repeated (see time_region)
+LAST_REGION = {}           # host-side time the last timed region spent ENQUEUEING its steps (per step)
 
 
 def time_region(fn, steps, warmup, barrier):
@@ -333,11 +334,14 @@ def time_region(fn, steps, warmup, barrier):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_cpu = time.perf_counter()
     for i in range(steps * reps):
         fn(warmup + i)
+    t_cpu = time.perf_counter() - t_cpu
     e1.record()
     torch.cuda.synchronize()
     barrier()
+    LAST_REGION["host_enqueue_us_per_step"] = 1e6 * t_cpu / (steps * reps)
     return e0.elapsed_time(e1) / 1e3 / reps
 
 
@@ -368,7 +372,8 @@ def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True,
         launches[i % nsets]()
 
     sec = time_region(one, steps, warmup, barrier)
-    res = {"sec": sec, "nsets": nsets, "launches_per_step": 1}
+    res = {"sec": sec, "nsets": nsets, "launches_per_step": 1,
+           "host_enqueue_us_per_step": LAST_REGION.get("host_enqueue_us_per_step")}
     if check_allreduce and world > 1:
         # the fused all-reduce against NCCL on the same step: complete the newest step's reduction
         # (deferred mode), then SUM-all-reduce the local fp64 sums of that step over NCCL
@@ -677,6 +682,7 @@ def main():
         "serialized": {"value": world * B * args.steps / ssec, "unit": "images/s", "ms_per_step": kernel_ms,
                        "per_rank_sec": per_rank(ser["sec"])},
         "per_rank_sec": per_rank(tr["sec"]),
+        "host_enqueue_us_per_step": tr.get("host_enqueue_us_per_step"),
         "e2e": {"value": world * B * args.steps / e2e_sec, "unit": "images/s",
                 "h2d_bytes_per_step": tr["h2d"], "d2h_bytes_per_step": tr["d2h"],
                 "numpy_in_value": world * B * args.steps / max_over_ranks(tr["e2e_numpy_in_sec"]),

@@ -948,22 +948,22 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
         if (!ok) status |= MBX_STATUS_INVALID_COST;
         block_sync<NWARPS>();   // the last walk's row4col / col4row are visible below
 
-        // ---- epilogue: mask, matched GT index, loss terms, gradients
-        if (!dep_done) {   // first global write of this CTA: the preceding grid must be complete (see above)
-            asm volatile("griddepcontrol.wait;" ::: "memory");
-            dep_done = true;
-        }
+        // ---- epilogue, part 1 (no global write yet): loss terms and gradients of this thread's columns in
+        // registers, block reduction of the loss sums -- all of it still overlaps the preceding grid
         double acc_sq = 0.0, acc_conf = 0.0;
         int n_match = 0;
+        float4 dlv[C];
+        float dcv[C];
+        int rv[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = tid + c * T;
+            dlv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            dcv[c] = 0.f;
+            rv[c] = -1;
             if (j >= P) continue;
             const int r = s.row4col[j];
-#ifndef MBX_PHASE_TIMING   // (timing builds use the mask buffer for the cycle counters)
-            if (p.mask) p.mask[row0 + j] = r >= 0 ? 1 : 0;
-#endif
-            if (p.gt_idx) p.gt_idx[row0 + j] = r;
+            rv[c] = r;
             n_match += r >= 0;
             const float ce = boundary ? cf[c] : __fadd_rn(cf[c], kEps32);
             // unmatched prior (almost all of them), unconditionally: -log((1 - c) + eps) and its derivative
@@ -996,14 +996,39 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             }
             acc_conf -= static_cast<double>(la);
             if (logits) dc = __fmul_rn(dc, __fmul_rn(cf[c], __fsub_rn(1.0f, cf[c])));
+            dlv[c] = dl;
+            dcv[c] = dc;
+        }
+        acc_sq = warp_sum(acc_sq);
+        acc_conf = warp_sum(acc_conf);
+        n_match = __reduce_add_sync(0xffffffffu, n_match);
+        if (lane == 0) {
+            s.red[warp] = acc_sq;
+            s.red[NWARPS + warp] = acc_conf;
+            s.ri[warp] = n_match;
+        }
+        block_sync<NWARPS>();
+        // ---- epilogue, part 2: the stores
+        if (!dep_done) {   // first global write of this CTA: the preceding grid must be complete (see above)
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            dep_done = true;
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = tid + c * T;
+            if (j >= P) continue;
+#ifndef MBX_PHASE_TIMING   // (timing builds use the mask buffer for the cycle counters)
+            if (p.mask) p.mask[row0 + j] = rv[c] >= 0 ? 1 : 0;
+#endif
+            if (p.gt_idx) p.gt_idx[row0 + j] = rv[c];
             if (nheads > 1) {   // gradients in the per-head layouts too
                 int hh;
                 const size_t e = head_elem(sh_heads, nheads, j, b, hh);
-                if (sh_heads[hh].dloc) st_stream_f4(reinterpret_cast<float4 *>(sh_heads[hh].dloc) + e, dl);
-                if (sh_heads[hh].dconf) sh_heads[hh].dconf[e] = dc;
+                if (sh_heads[hh].dloc) st_stream_f4(reinterpret_cast<float4 *>(sh_heads[hh].dloc) + e, dlv[c]);
+                if (sh_heads[hh].dconf) sh_heads[hh].dconf[e] = dcv[c];
             } else {
-                if (p.d_loc) st_stream_f4(reinterpret_cast<float4 *>(p.d_loc) + row0 + j, dl);
-                if (p.d_conf) p.d_conf[row0 + j] = dc;
+                if (p.d_loc) st_stream_f4(reinterpret_cast<float4 *>(p.d_loc) + row0 + j, dlv[c]);
+                if (p.d_conf) p.d_conf[row0 + j] = dcv[c];
             }
         }
         if (p.stacked && !failed) {
@@ -1015,15 +1040,6 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
                 reinterpret_cast<float4 *>(p.stacked)[off + rank] = s.gt[i];
             }
         }
-        acc_sq = warp_sum(acc_sq);
-        acc_conf = warp_sum(acc_conf);
-        n_match = __reduce_add_sync(0xffffffffu, n_match);
-        if (lane == 0) {
-            s.red[warp] = acc_sq;
-            s.red[NWARPS + warp] = acc_conf;
-            s.ri[warp] = n_match;
-        }
-        block_sync<NWARPS>();
         if (tid == 0) {
             double a = 0.0, cc = 0.0;
             int m = 0;
@@ -1042,7 +1058,10 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     }
 
     if (!dep_done) asm volatile("griddepcontrol.wait;" ::: "memory");   // (a CTA that solved no image)
-    if (status) atomicOr(p.status, status);
+    if (status) {
+        atomicOr(p.status, status);
+        __threadfence();
+    }
 #ifdef MBX_PHASE_TIMING
     MBX_T(7);   // epilogue
     t_acc[9] = __reduce_add_sync(0xffffffffu, static_cast<int>(t_acc[9]));   // exact cost evaluations of the warp
@@ -1057,17 +1076,19 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     }
 #endif
 
-    // ---- last CTA to finish reduces the per-image partials in a fixed order
+    // ---- last CTA to finish reduces the per-image partials in a fixed order.  Thread 0 wrote this CTA's
+    // partials itself; its acq_rel ticket atomic publishes them (and, through the barrier, whatever the other
+    // threads' status atomics did) and acquires the other CTAs' -- no block-wide __threadfence, which would
+    // wait for every thread's gradient stores to drain, on the one chain that is not overlapped.
     __shared__ bool is_last;
-    __threadfence();
     block_sync<NWARPS>();
     if (tid == 0) {
-        const unsigned t = atomicAdd(p.ticket, 1u);
+        unsigned t;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(p.ticket) : "memory");
         is_last = (t == gridDim.x - 1);
     }
     block_sync<NWARPS>();
     if (!is_last) return;
-    __threadfence();
     // status word and previous launch sequence number: loaded together with the partials
     const TailPrefetch pre = tail_prefetch(p);
     double a = 0.0, cc = 0.0, md = 0.0;
