@@ -10,7 +10,8 @@
  * Conventions (all functions):
  *   - every pointer is a DEVICE pointer into memory owned by the caller
  *     (PyTorch); the library allocates nothing persistent and keeps no global
- *     state besides the thread-local error string;
+ *     state besides the thread-local error string, per-device launch-attribute
+ *     caches and a thread-local launch counter per workspace (see MBX_FLAG_PDL);
  *   - tensors are dense, row-major, float32 / int32 unless said otherwise and
  *     16-byte aligned;
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
@@ -70,9 +71,12 @@ extern "C" {
                                        previous step, or inputs staged in pinned host memory).  The kernel may then
                                        start while that preceding kernel is still running and waits for it
                                        (griddepcontrol.wait) only before its first write to outputs / workspace:
-                                       consecutive steps overlap launch latency and tail.  Results are identical.
-                                       Ignored with stacked_gt / n_stacked, dynamic scheduling (B above the resident
-                                       CTAs) and MBX_FLAG_GENERIC. */
+                                       consecutive steps overlap launch latency, tail and head.  Results are
+                                       identical.  Works with static and dynamic image scheduling (the library keeps
+                                       a per-thread launch counter per workspace to alternate between two scheduler
+                                       slots) and with the fused all-reduce (deferred mode then reports the global
+                                       sums two steps back).  Ignored with stacked_gt / n_stacked (a scan kernel
+                                       runs in front) and MBX_FLAG_GENERIC.  mbx_detect honours it as well. */
 #define MBX_FLAG_GENERIC       4u   /* force the generic shared-memory matching kernel (any P) instead
                                        of the register-resident family (tuning / testing) */
 #define MBX_FLAG_WARPS_SHIFT   8    /* bits 8..15: force CTA size in warps (0 = heuristic) */
