@@ -366,6 +366,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
         __threadfence();
         if (tid == 0) st_release_gpu(p.oready, p.launch_id);
     }
+    unsigned ar_seq_hint = 0xffffffffu;
     bool order_seen = !dyn;
     for (int q = is_poster ? p.B : static_cast<int>(blockIdx.x); q < p.B;) {
         int b = q;
@@ -1013,6 +1014,9 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             asm volatile("griddepcontrol.wait;" ::: "memory");
             dep_done = true;
         }
+        // (fused all-reduce: the step counter is final once the preceding grid is complete; whoever turns out
+        // to be the last CTA then knows the step to collect before it has reduced anything)
+        if (p.ar_world > 1 && tid == 0) ar_seq_hint = __ldcg(p.ar_seq);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = tid + c * T;
@@ -1091,6 +1095,14 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     if (!is_last) return;
     // status word and previous launch sequence number: loaded together with the partials
     const TailPrefetch pre = tail_prefetch(p);
+    CollectPrefetch cpf;
+    cpf.step = 0xffffffffu;
+    if (warp == 0 && p.ar_world > 1) {   // the collect's words, requested in the same round as the partials
+        const unsigned sh = __shfl_sync(0xffffffffu, ar_seq_hint, 0);
+        const bool deferred = (p.flags & MBX_FLAG_AR_DEFERRED) != 0;
+        const unsigned lag = deferred ? ((p.flags & MBX_FLAG_PDL) ? 2u : 1u) : 0u;
+        cpf = ar_collect_prefetch(p.ar_peer, p.ar_world, p.ar_rank, (sh != 0xffffffffu && sh >= lag) ? sh - lag : 0xffffffffu);
+    }
     double a = 0.0, cc = 0.0, md = 0.0;
     for (int b = tid; b < p.B; b += T) {
         a += __ldcg(p.partials + 2 * b);
@@ -1114,7 +1126,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             Cc += s.red[NWARPS + w];
             Mt += s.red[2 * NWARPS + w];
         }
-        finalize_losses(p, A, Cc, Mt, pre);   // warp-cooperative (lane r posts to peer r)
+        finalize_losses(p, A, Cc, Mt, pre, &cpf);   // warp-cooperative (lane r posts to peer r)
     }
 }
 
