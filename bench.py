@@ -282,7 +282,7 @@ def run_reference(args):
         "impl": "reference", "metric": "match+loss images/sec", "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": train_config_dict(parts[0], args.gpus, cold="n/a (CPU)"),
+        "config": train_config_dict(parts[0], args.gpus),
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": "each step = the full global batch of %d images (%d per GPU x %d), sharded by "
                                    "image over %d processes; numpy/scipy oracle port of reference loss.py:8-117"
@@ -299,13 +299,30 @@ def run_reference(args):
     return 0
 
 
-def train_config_dict(d, n_gpus, cold):
+def train_nsets(d):
+    """Device-resident input sets the GPU arm rotates over (> 2x L2 worth of inputs)."""
+    B, P, M = d["B"], d["P"], d["M"]
+    per_set = 4 * (B * P * 4 + B * P + B * M * 4 + B)
+    return max(2, min(1024, (2 * L2_BYTES) // per_set + 1))
+
+
+def train_config_dict(d, n_gpus):
+    """The `config` object of the bench line -- the SAME dict from both arms (the reference arm runs the same
+    workload on the host; the cache / launch entries describe how the GPU arm keeps its timing honest)."""
     return {"workload": "BASELINE configs[1]: Inception-ResNet-v2 299x299 multibox head outputs (random init), "
                         "5 aspect ratios, P=%d priors, batch %d per GPU, MAX_NUM_BBOXES=%d: GT->prior matching + "
                         "location/confidence loss fwd/bwd" % (d["P"], d["B"], d["M"]),
             "K": d["K"], "P": d["P"], "batch_per_gpu": d["B"], "global_batch": d["B"] * n_gpus, "M": d["M"],
             "alpha": d["alpha"], "mean_gt_per_image": float(d["num_gt"].mean()),
-            "parallelism": "image-sharded x%d" % n_gpus, "cache": cold}
+            "parallelism": "image-sharded x%d" % n_gpus,
+            "cache": "GPU arm: inputs rotate over %d device-resident sets (> 2x L2) so no step finds its inputs in L2"
+                     % train_nsets(d),
+            "launch": "GPU arm: one kernel per step, launched back to back with programmatic dependent launch "
+                      "(MBX_FLAG_PDL): step k+1's load / logs / assignment solve start while step k's "
+                      "stores, last-CTA reduction and completion are still in flight; every write of "
+                      "step k+1 (gradients, losses, workspace) waits for step k (griddepcontrol.wait). "
+                      "All K steps do all their work inside the timed region; the 'serialized' object is "
+                      "the same loop without the overlap"}
 
 
 # ----------------------------------------------------------------------------- GPU legs
@@ -352,8 +369,7 @@ def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True,
     from multibox_b200 import loss
     B, P, M = d["B"], d["P"], d["M"]
     dev = torch.device("cuda", torch.cuda.current_device())
-    per_set = 4 * (B * P * 4 + B * P + B * M * 4 + B)
-    nsets = max(2, min(1024, (2 * L2_BYTES) // per_set + 1))
+    nsets = train_nsets(d)
     t = {k: torch.from_numpy(np.ascontiguousarray(d[k])).to(dev) for k in ("locations", "confidences", "gt", "num_gt")}
     locs = rotated_sets(t["locations"], nsets)
     confs = rotated_sets(t["confidences"].view(B, P), nsets)
@@ -671,14 +687,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
         "timed_steps": args.steps * max(1, -(-MIN_TIMED_STEPS // max(1, args.steps))),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(train_config_dict(d, world, cold="inputs rotate over %d device-resident sets (> 2x L2) so no step "
-                                                          "finds its inputs in L2" % tr["nsets"]),
-                       launch="one kernel per step, launched back to back with programmatic dependent launch "
-                              "(MBX_FLAG_PDL): step k+1's load / logs / assignment solve start while step k's "
-                              "epilogue, last-CTA reduction and completion are still in flight; every write of "
-                              "step k+1 (gradients, losses, workspace) waits for step k (griddepcontrol.wait). "
-                              "All K steps do all their work inside the timed region; the 'serialized' object is "
-                              "the same loop without the overlap"),
+        "config": train_config_dict(d, world),
         "serialized": {"value": world * B * args.steps / ssec, "unit": "images/s", "ms_per_step": kernel_ms,
                        "per_rank_sec": per_rank(ser["sec"])},
         "per_rank_sec": per_rank(tr["sec"]),
