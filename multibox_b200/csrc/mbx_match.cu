@@ -206,6 +206,9 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_kernel(const Match
     }
     bool priors_ready = !has_priors;
     int pbuf = 0;
+    // fused all-reduce: every launch takes a ticket (the register-resident family derives the step its
+    // collector CTA pulls from it; this kernel has no collector and completes the reduction in its tail)
+    if (p.ar_world > 1 && blockIdx.x == 0 && tid == 0) (void)ar_take_ticket(p);
 
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         const float4 *gg;
@@ -490,7 +493,6 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_kernel(const Match
     }
     __syncthreads();
     if (warp == 0) {
-        if (p.ar_world > 1 && (p.flags & MBX_FLAG_AR_DEFERRED)) ar_post_pending(p);   // no poster CTA here
         double A = 0.0, C = 0.0, Mt = 0.0;
         for (int w = 0; w < NWARPS; ++w) {
             A += s.red[w];
@@ -700,14 +702,13 @@ extern "C" int mbx_match_loss_heads(const mbx_heads *heads, const float *gt_bbox
 extern "C" size_t mbx_allreduce_buffer_bytes(void) { return align_up(kArBytes, 256); }
 
 namespace mbx {
-__global__ void mbx_allreduce_flush_kernel(MatchParams p) {
-    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+__global__ void mbx_allreduce_flush_kernel(MatchParams p) {   // one warp
     const unsigned seq = *p.ar_seq;
     if (seq == 0u) return;
-    ar_post_pending(p);                      // deferred mode: the newest step has not been sent yet
-    if (threadIdx.x != 0) return;
     double g_loc = 0.0, g_conf = 0.0;
-    if (ar_collect(p.ar_peer, p.ar_world, p.ar_rank, seq - 1u, g_loc, g_conf)) {
+    const bool ok = ar_pull_warp(p, seq - 1u, g_loc, g_conf);   // every rank's newest step, from its outbox
+    if (threadIdx.x != 0) return;
+    if (ok) {
         double *r64 = reinterpret_cast<double *>(p.results);
         r64[4] = g_loc;
         r64[5] = g_conf;

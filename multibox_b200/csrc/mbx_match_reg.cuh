@@ -326,11 +326,20 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     for (int c = 0; c < C; ++c)
         if (tid + c * T >= P) invalid_mask |= 1u << c;
 
-    // Deferred fused all-reduce: the launch appends one extra CTA that only sends the previous
-    // step's loss sums to the peers (NVLink latency overlaps this kernel's work).
+    // Deferred fused all-reduce: the launch appends one extra CTA, the COLLECTOR, which pulls the peers' loss
+    // sums of an earlier step over NVLink while the other CTAs solve (mbx_match.cuh).
     const bool has_poster = p.ar_world > 1 && (p.flags & MBX_FLAG_AR_DEFERRED);
     const int n_work = has_poster ? static_cast<int>(gridDim.x) - 1 : static_cast<int>(gridDim.x);
     const bool is_poster = has_poster && static_cast<int>(blockIdx.x) == n_work;
+    // Launch ticket = step index of this launch in the all-reduce (world > 1): taken by ONE CTA (the collector,
+    // else CTA 0) BEFORE it lets the next launch start, so overlapping launches take theirs in stream order.
+    unsigned my_step = 0xffffffffu;
+    if (p.ar_world > 1 && static_cast<int>(blockIdx.x) == (has_poster ? n_work : 0)) {
+        __shared__ unsigned sh_step;
+        if (tid == 0) sh_step = ar_take_ticket(p);
+        block_sync<NWARPS>();
+        my_step = sh_step;
+    }
     // Programmatic dependent launch (MBX_FLAG_PDL; the launcher sets the stream-serialization attribute):
     // this grid may start while the preceding kernel of the stream -- the previous training step -- is
     // still running; the next one may start as soon as every CTA of this grid is running.  The caller
@@ -342,13 +351,30 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     const bool pdl = (p.flags & MBX_FLAG_PDL) != 0;
     bool dep_done = !pdl;
     if (pdl) {
-        asm volatile("griddepcontrol.launch_dependents;");
-        if (is_poster || (logits && p.conf_out)) {   // (these write before the epilogue)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (logits && p.conf_out && !is_poster) {   // (writes before the epilogue)
             asm volatile("griddepcontrol.wait;" ::: "memory");
             dep_done = true;
         }
     }
-    if (is_poster && warp == 0) ar_post_pending(p);
+    if (is_poster) {
+        // The peers' words are self-validating (tag == step + 1) and live in THEIR outboxes, which this launch
+        // only reads: nothing here depends on the preceding launch, so the NVLink round trips happen before
+        // griddepcontrol.wait, while everybody else solves.  Only the hand-off to the last CTA comes after it.
+        Gsum gs;
+        gs.loc = gs.conf = 0.0;
+        gs.tag = 0u;
+        if (warp == 0) {
+            const unsigned lag = pdl ? 2u : 1u;
+            if (my_step != 0xffffffffu && my_step >= lag && ar_pull_warp(p, my_step - lag, gs.loc, gs.conf))
+                gs.tag = my_step - lag + 1u;
+        }
+        if (!dep_done) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            dep_done = true;
+        }
+        if (tid == 0) ar_store_gsum(p, gs);   // (published by this thread's ticket atomic below)
+    }
 
     // Image scheduling.  Static (image = CTA index, stride = resident CTAs) when every image has
     // its own CTA; otherwise DYNAMIC over the heavy-first order built by mbx_order_kernel: the
@@ -1097,11 +1123,10 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     const TailPrefetch pre = tail_prefetch(p);
     CollectPrefetch cpf;
     cpf.step = 0xffffffffu;
-    if (warp == 0 && p.ar_world > 1) {   // the collect's words, requested in the same round as the partials
+    if (warp == 0 && p.ar_world > 1 && !(p.flags & MBX_FLAG_AR_DEFERRED)) {
+        // blocking mode: the collect's words, requested in the same round as the partials
         const unsigned sh = __shfl_sync(0xffffffffu, ar_seq_hint, 0);
-        const bool deferred = (p.flags & MBX_FLAG_AR_DEFERRED) != 0;
-        const unsigned lag = deferred ? ((p.flags & MBX_FLAG_PDL) ? 2u : 1u) : 0u;
-        cpf = ar_collect_prefetch(p.ar_peer, p.ar_world, p.ar_rank, (sh != 0xffffffffu && sh >= lag) ? sh - lag : 0xffffffffu);
+        cpf = ar_collect_prefetch(p.ar_peer, p.ar_world, p.ar_rank, sh);
     }
     double a = 0.0, cc = 0.0, md = 0.0;
     for (int b = tid; b < p.B; b += T) {
@@ -1119,7 +1144,6 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     }
     block_sync<NWARPS>();
     if (warp == 0) {
-        if (!has_poster && p.ar_world > 1 && (p.flags & MBX_FLAG_AR_DEFERRED)) ar_post_pending(p);
         double A = 0.0, Cc = 0.0, Mt = 0.0;
         for (int w = 0; w < NWARPS; ++w) {
             A += s.red[w];

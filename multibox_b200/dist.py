@@ -124,8 +124,9 @@ class PeerAllreduce:
     """Peer-memory plumbing for the all-reduce that is FUSED into the matching/loss kernel
     (mbx_match_loss_allreduce): one small symmetric buffer per rank, mapped into every
     process of the NVLink box through torch's symmetric memory (CUDA VMM handles exchanged
-    over the process group).  PyTorch only allocates and maps; the exchange itself is plain
-    peer stores + a system-scope atomic inside the kernel's last CTA."""
+    over the process group).  PyTorch only allocates and maps; the exchange itself happens inside
+    the kernel: tagged 8-byte words, pushed into the peers' tables (blocking mode) or left in the
+    rank's own outbox and pulled by the peers' collector CTAs over NVLink (deferred mode)."""
 
     def __init__(self, group=None, device=None):
         import ctypes
@@ -156,9 +157,10 @@ class PeerAllreduce:
         self._keep = (buf, hdl)
 
     def reset(self):
-        """Collective: re-zeroes every rank's symmetric buffer (step counters, arrival counters, slot
-        ring).  Call on ALL ranks after a step reported MBX_STATUS_AR_TIMEOUT -- the ranks' counters are
-        out of step after a timeout and every later reduction would stay wrong -- with no step in flight."""
+        """Collective: re-zeroes every rank's symmetric buffer (step counters, launch tickets, the sticky
+        timeout flag, outbox and table rings).  Call on ALL ranks after a step reported
+        MBX_STATUS_AR_TIMEOUT -- the ranks' counters are out of step after a timeout; until the reset every
+        later reduction fails at once instead of waiting again -- with no step in flight."""
         if self.world == 1:
             return
         buf = self._keep[0]
@@ -167,3 +169,38 @@ class PeerAllreduce:
         buf.zero_()
         torch.cuda.synchronize(buf.device)
         dist.barrier(self.group)
+
+
+class LoopbackPeers:
+    """`world` ranks of the fused all-reduce emulated on ONE device: the symmetric buffers are plain device
+    allocations of this process and `rank(r)` is the `peer=` object of rank r.  The kernels cannot tell the
+    difference (they only see the pointer table), so the whole exchange protocol -- tickets, outboxes,
+    collector CTA, rings, the timeout flag -- runs on a single-GPU box (tests/test_gpu_loopback.py).
+    Deferred-mode ranks may share a stream (no rank waits for a same-step peer); blocking-mode ranks
+    need one stream each, because a rank's kernel spins until every other rank's kernel has posted."""
+
+    class _Rank:
+        def __init__(self, ptr_array, world, rank):
+            self.ptr_array, self.world, self.rank = ptr_array, world, rank
+
+    def __init__(self, world, device=None):
+        import ctypes
+        from . import _lib
+        if not 2 <= world <= _lib.MAX_PEERS:
+            raise ValueError("world must be 2..%d" % _lib.MAX_PEERS)
+        lib = _lib.load()
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        nbytes = int(lib.mbx_allreduce_buffer_bytes())
+        self.bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=device) for _ in range(world)]
+        self.world = world
+        self.ptr_array = (ctypes.c_ulonglong * world)(*[b.data_ptr() for b in self.bufs])
+        torch.cuda.synchronize(device)
+
+    def rank(self, r):
+        return LoopbackPeers._Rank(self.ptr_array, self.world, r)
+
+    def reset(self):
+        torch.cuda.synchronize(self.bufs[0].device)
+        for b in self.bufs:
+            b.zero_()
+        torch.cuda.synchronize(self.bufs[0].device)
