@@ -362,6 +362,20 @@ def time_region(fn, steps, warmup, barrier):
     return e0.elapsed_time(e1) / 1e3 / reps
 
 
+_PIPE_PEERS = []
+
+
+def pipe_peer(r, peer):
+    """The r-th PeerAllreduce of the pipelined host-buffer steps (one exchange state per stream; created
+    once, in the same order on every rank, and reused by every bench object)."""
+    if peer is None or peer.world == 1:
+        return None
+    from multibox_b200 import dist as mdist
+    while len(_PIPE_PEERS) <= r:
+        _PIPE_PEERS.append(mdist.PeerAllreduce())
+    return _PIPE_PEERS[r]
+
+
 def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True, check_allreduce=False,
                 static_schedule=False):
     """Device-resident steps (value) and host-buffer steps (e2e) of match + loss fwd/bwd on batch `d`."""
@@ -424,8 +438,9 @@ def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True,
             np.copyto(hs.h_gt.numpy(), roll[r]["gt"])
             np.copyto(hs.h_ng.numpy(), roll[r]["num_gt"])
 
-        def wall(fn, n, drain=None):
-            for i in range(max(warmup, hsets)):
+        def wall(fn, n, drain=None, nwarm=hsets):
+            nwarm = max(warmup, nwarm)       # (every rotating object has run once before the timed region)
+            for i in range(nwarm):
                 fn(i)
             if drain:
                 drain()
@@ -434,7 +449,7 @@ def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True,
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for i in range(n * reps):
-                fn(max(warmup, hsets) + i)
+                fn(nwarm + i)
             if drain:
                 drain()
             torch.cuda.synchronize()
@@ -451,29 +466,39 @@ def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True,
         res["e2e_serial_sec"] = wall(e2e_serial, steps)
         res["last"] = last["v"]
         res["last_global"] = ser[last["i"] % hsets].flush()
-        # (b) THREE steps in flight (four rotating step objects): steps k+1 .. k+3 are submitted (their
-        # zero-copy PCIe reads and solves overlap the tail of step k: programmatic dependent launch) before the
-        # host polls step k's result block -- a single host-buffer step has ~37 us of latency (launch, PCIe
-        # reads, solve, result write-back), so throughput is that latency divided by the steps in flight
-        pipe = make(False, True)
+        # (b) SEVERAL steps in flight: rotating step objects, each with a CUDA stream of its own
+        # (own_stream=True).  submit = ONE foreign call that enqueues {H2D copy of the packed pinned inputs on
+        # the copy engine, the kernel} on the object's stream; the copy of step k+1 overlaps the kernels of the
+        # steps before it, and the host only polls the mapped result block of the OLDEST step.  A single
+        # host-buffer step has ~35 us of latency (launch, PCIe, solve, result write-back); profiles/e2e_depth.py
+        # measured the depth sweep (round 2: kernel-streamed zero-copy inputs under PDL level off at 15.2 us per
+        # step, copy engine + own streams at 13.0 us with seven steps in flight).  With a fused all-reduce every
+        # object has its own PeerAllreduce (steps on different streams cannot share one exchange state).
+        npipe = 8 if B * P * 20 < (4 << 20) else 4
+        pipe = []
+        for r in range(npipe):
+            hs = loss.MultiboxLossStep(B, P, M, d["priors"], d["alpha"], device=dev, peer=pipe_peer(r, peer),
+                                       deferred_allreduce=True, host_results=True, own_stream=True)
+            stage(hs, r % hsets)
+            pipe.append(hs)
         pend = []
 
         def e2e_pipe(i, numpy_in=False):
-            hs = pipe[i % hsets]
+            hs = pipe[i % npipe]
             if numpy_in:                      # a caller that holds plain numpy arrays pays this staging copy
                 stage(hs, i % hsets)
             hs.submit_pinned()
             pend.append(hs)
-            if len(pend) > hsets - 1:         # hsets - 1 = 3 steps in flight
+            if len(pend) > npipe - 1:         # npipe - 1 steps stay in flight
                 last["p"] = pend.pop(0).wait(validate=True)
 
         def drain():
             while pend:
                 last["p"] = pend.pop(0).wait(validate=True)
 
-        res["e2e_sec"] = wall(e2e_pipe, steps, drain)
-        res["e2e_numpy_in_sec"] = wall(lambda i: e2e_pipe(i, True), steps, drain)
-        res.update(h2d=pipe[0].h2d_bytes, d2h=pipe[0].d2h_bytes, last_pipe=last["p"])
+        res["e2e_sec"] = wall(e2e_pipe, steps, drain, nwarm=npipe)
+        res["e2e_numpy_in_sec"] = wall(lambda i: e2e_pipe(i, True), steps, drain, nwarm=npipe)
+        res.update(h2d=pipe[0].h2d_bytes, d2h=pipe[0].d2h_bytes, last_pipe=last["p"], steps_in_flight=npipe - 1)
     return res
 
 
@@ -696,22 +721,24 @@ def main():
                 "h2d_bytes_per_step": tr["h2d"], "d2h_bytes_per_step": tr["d2h"],
                 "numpy_in_value": world * B * args.steps / max_over_ranks(tr["e2e_numpy_in_sec"]),
                 "one_in_flight_value": world * B * args.steps / max_over_ranks(tr["e2e_serial_sec"]),
-                "how": "MultiboxLossStep(host_results=True, zero_copy=True, pdl=True), THREE steps in flight "
-                       "(submit_pinned / wait on four rotating step objects): each step's inputs sit in one packed PINNED "
-                       "host buffer (already staged there: 'value'; np.copyto of the caller's numpy arrays into it "
-                       "inside the timed loop: 'numpy_in_value'); ONE kernel per step streams them over PCIe itself "
-                       "(read-once 16-byte loads from the mapped buffer: the host->device transfer happens inside the "
-                       "kernel, h2d_bytes_per_step bytes every step), solves, and stores the 64-byte loss/status block "
-                       "straight into mapped pinned host memory (loss all-reduce fused in when N > 1); the host submits "
-                       "step k+3, then polls step k's launch sequence word and checks its status, every step; gradients "
-                       "stay on the device for the backward pass; wall clock.  'one_in_flight_value' = submit, poll, "
-                       "next (CUDA graph of the one kernel; the round-1 mode)"},
+                "steps_in_flight": tr["steps_in_flight"],
+                "how": "MultiboxLossStep(host_results=True, own_stream=True): rotating step objects, each with its own "
+                       "CUDA stream, SEVEN steps in flight (submit_pinned / wait).  Each step's inputs sit in one packed "
+                       "PINNED host buffer (already staged there: 'value'; np.copyto of the caller's numpy arrays into it "
+                       "inside the timed loop: 'numpy_in_value'); submit is ONE foreign call (mbx_match_plan_launch_staged) "
+                       "that enqueues the H2D copy of h2d_bytes_per_step bytes and the ONE kernel of the step on the "
+                       "object's stream, every step; the kernel solves and stores the 64-byte loss/status block straight "
+                       "into mapped pinned host memory (loss all-reduce fused in when N > 1, one exchange state per "
+                       "object); the host polls the OLDEST step's launch sequence word and checks its status, every step; "
+                       "gradients stay on the device for the backward pass; wall clock.  'one_in_flight_value' = submit, "
+                       "poll, next (CUDA graph of one kernel that streams the inputs over PCIe itself; the round-1 mode)"},
         "gpu_launches": tr["launches_per_step"] * args.steps,
-        "collective": ("loss SUM all-reduce fused into the kernel (NVLink peer stores + system-scope arrival "
-                       "counters, 4-deep slot ring); step k posts its sums and completes step k-1's reduction, the "
-                       "last step is flushed after the timed region; no NCCL call per step; allreduce_check = the "
-                       "fused global sums of the last step against an NCCL all-reduce of the ranks' local fp64 sums"
-                       ) if world > 1 else None,
+        "collective": ("loss SUM all-reduce fused into the kernel over NVLink peer memory (tagged 8-byte words, no "
+                       "fence / remote atomic): step k leaves its sums in its own outbox and completes step k-2's "
+                       "reduction (k-1's without PDL) from the words one extra CTA pulled from the peers' outboxes "
+                       "while the others solved; the last step is flushed after the timed region; no NCCL call per "
+                       "step; allreduce_check = the fused global sums of the last step against an NCCL all-reduce of "
+                       "the ranks' local fp64 sums") if world > 1 else None,
         "allreduce_check": tr.get("allreduce_check"),
         "last_losses": {"local": tr.get("last"), "global": tr.get("last_global"), "pipelined_local": tr.get("last_pipe")},
         "roofline": {"bound": "hbm", "kernel": "mbx_match_loss_reg_kernel", "achieved": achieved, "peak": peak,

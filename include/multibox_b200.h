@@ -192,18 +192,23 @@ int mbx_match_loss_heads(const mbx_heads *heads,
 /* Same as mbx_match_loss, with the SUM all-reduce of the two loss scalars over the
  * `world` GPUs of one NVLink box FUSED into the kernel (reference semantics: the losses
  * are batch sums, loss.py:100-101; the batch is sharded by image, one process per GPU).
- * The last CTA stores its sums into every rank's slot table through peer memory
- * (NVLink P2P stores), signals arrival with a system-scope atomic, waits for the other
- * ranks and adds the slots in rank order; results[8..13] then hold the global sums,
- * bit-identical on every rank.  Every rank must call this once per step, in step order.
+ * Messages are four 8-byte words {32 payload bits, 32-bit tag = step + 1} per rank and step, valid exactly
+ * when the tag matches (no system-scope fence, no remote atomic, no acknowledgement).  Blocking mode
+ * (default): the last CTA stores its words into every rank's table through peer memory (NVLink P2P
+ * stores), waits for the other ranks' words of the same step and adds them in rank order; results[8..13]
+ * then hold the global sums, bit-identical on every rank.  Every rank must call this once per step, in
+ * step order.
  *   peer_buffers [world]  HOST array of device pointers: rank r's symmetric buffer of
  *                         mbx_allreduce_buffer_bytes() bytes (zero-filled once), mapped
  *                         into this process (CUDA IPC / VMM; torch symmetric memory)
- * With MBX_FLAG_AR_DEFERRED the step posts its own sums and completes the PREVIOUS step's
- * reduction instead (results[14] = index of the step the global sums belong to, -1 = none
- * yet): no rank waits for a slower peer inside the step; mbx_allreduce_flush completes the
- * newest step on demand.
- * A rank that never arrives trips MBX_STATUS_AR_TIMEOUT (~2 s) instead of hanging. */
+ * With MBX_FLAG_AR_DEFERRED the step leaves its sums in its OWN outbox (local stores: no NVLink traffic on
+ * the kernel's tail) and completes an EARLIER step's reduction instead -- the previous one, or the one
+ * before it under MBX_FLAG_PDL -- whose words one extra CTA of the launch (the collector) pulls from the
+ * peers' outboxes over NVLink while the other CTAs solve; results[14] = index of the step the global sums
+ * belong to, -1 = none yet.  No rank waits for a slower peer inside the step; mbx_allreduce_flush completes
+ * the newest step on demand.
+ * A rank that never arrives trips MBX_STATUS_AR_TIMEOUT (~2 s) instead of hanging; the condition is
+ * sticky (later steps report it at once) until the buffers are zero-filled again with no step in flight. */
 size_t mbx_allreduce_buffer_bytes(void);
 int mbx_allreduce_flush(float *results, void *workspace, size_t workspace_bytes,
                         const unsigned long long *peer_buffers, int world, int rank, void *stream);
@@ -238,6 +243,13 @@ int  mbx_match_plan_create(mbx_match_plan **plan,
                            void *workspace, size_t workspace_bytes,
                            const unsigned long long *peer_buffers, int world, int rank);
 int  mbx_match_plan_launch(const mbx_match_plan *plan, void *stream);
+/* Host-buffer step in ONE foreign call: cudaMemcpyAsync(dev_dst, host_src, nbytes, HostToDevice, stream)
+ * followed by mbx_match_plan_launch(plan, stream).  `host_src` is the caller's (pinned) packed input
+ * buffer, `dev_dst` the device buffer the plan's input pointers point into.  Steps enqueued on different
+ * streams overlap one step's copy with another step's kernel (multibox_b200/loss.py MultiboxLossStep
+ * (own_stream=True)). */
+int  mbx_match_plan_launch_staged(const mbx_match_plan *plan, const void *host_src, void *dev_dst,
+                                  size_t nbytes, void *stream);
 void mbx_match_plan_destroy(mbx_match_plan *plan);
 
 /* ------------------------------------------------------------------------- *

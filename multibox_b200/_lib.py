@@ -35,7 +35,7 @@ RESULT_WORDS = 16
 EXPORTS = ("mbx_version", "mbx_last_error", "mbx_device_info",
            "mbx_match_workspace_bytes", "mbx_match_loss", "mbx_match_loss_ragged", "mbx_match_loss_heads",
            "mbx_allreduce_buffer_bytes", "mbx_match_loss_allreduce", "mbx_allreduce_flush",
-           "mbx_match_plan_create", "mbx_match_plan_launch", "mbx_match_plan_destroy",
+           "mbx_match_plan_create", "mbx_match_plan_launch", "mbx_match_plan_launch_staged", "mbx_match_plan_destroy",
            "mbx_detect_workspace_bytes", "mbx_detect", "mbx_detect_heads",
            "mbx_filter_proposals", "mbx_convert_proposals",
            "mbx_debug_nplog", "mbx_debug_cost_matrix", "mbx_debug_sqrt_mismatches", "mbx_debug_fastlog_violations")
@@ -118,6 +118,8 @@ def load():
         [_c_void_p, _c_int, _c_int]
     lib.mbx_match_plan_launch.restype = _c_int
     lib.mbx_match_plan_launch.argtypes = [_c_void_p, _c_void_p]
+    lib.mbx_match_plan_launch_staged.restype = _c_int
+    lib.mbx_match_plan_launch_staged.argtypes = [_c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]
     lib.mbx_match_plan_destroy.restype = None
     lib.mbx_match_plan_destroy.argtypes = [_c_void_p]
     lib.mbx_allreduce_flush.restype = _c_int

@@ -808,6 +808,21 @@ extern "C" int mbx_match_plan_launch(const mbx_match_plan *pl, void *stream) {
                            pl->workspace_bytes, pl->world > 1 ? pl->peers : nullptr, pl->world, pl->rank, stream);
 }
 
+extern "C" int mbx_match_plan_launch_staged(const mbx_match_plan *pl, const void *host_src, void *dev_dst,
+                                            size_t nbytes, void *stream) {
+    if (!pl || (nbytes > 0 && (!host_src || !dev_dst))) {
+        set_error("mbx_match_plan_launch_staged: null plan / buffer");
+        return MBX_E_ARG;
+    }
+    if (nbytes > 0) {
+        if (int e = check_cuda(cudaMemcpyAsync(dev_dst, host_src, nbytes, cudaMemcpyHostToDevice,
+                                               static_cast<cudaStream_t>(stream)),
+                               "cudaMemcpyAsync(staged inputs)"))
+            return e;
+    }
+    return mbx_match_plan_launch(pl, stream);
+}
+
 extern "C" void mbx_match_plan_destroy(mbx_match_plan *pl) { delete pl; }
 
 int mbx::match_loss_impl(const mbx_heads *heads, const float *locations, const float *confidences,

@@ -462,7 +462,7 @@ class MultiboxLossStep:
 
     def __init__(self, B, P, M, priors, alpha, device="cuda", logits=False, want_mask=False,
                  want_stacked=False, warps=0, use_graph=False, peer=None, deferred_allreduce=False,
-                 host_results=False, zero_copy=False, pdl=False, static_schedule=False):
+                 host_results=False, zero_copy=False, pdl=False, static_schedule=False, own_stream=False):
         self.B, self.P, self.M, self.alpha = B, P, M, float(alpha)
         self.device = torch.device(device)
         if self.device.index is None:
@@ -518,6 +518,19 @@ class MultiboxLossStep:
             self._res_u32 = self.h_res.numpy().view("uint32")
             self._res_f32 = self.h_res.numpy()
             self._res_u32[15] = 0
+        # own_stream: the object's host-buffer steps run on a CUDA stream of its own -- ONE foreign call
+        # enqueues the H2D copy of the packed pinned inputs (copy engine, full PCIe rate) and the kernel
+        # (mbx_match_plan_launch_staged).  A caller that rotates a few such objects overlaps the copy of step
+        # k+1 with the kernel of step k without any event plumbing.  Host-buffer path with host_results only.
+        # With a fused all-reduce every object needs its OWN PeerAllreduce (steps on different streams must
+        # not share one exchange state).
+        self.stream = None
+        if own_stream:
+            if not self.host_results or self.zero_copy or use_graph:
+                raise ValueError("own_stream needs host_results=True, zero_copy=False, use_graph=False")
+            self.flags &= ~_lib.FLAG_PDL          # (the kernel follows a copy on its stream, not a kernel)
+            self.stream = torch.cuda.Stream(device=self.device)
+            self._staged = None
 
     def _views(self, buf):
         (a0, n0), (a1, n1), (a2, n2), (a3, n3) = self._sections
@@ -579,9 +592,15 @@ class MultiboxLossStep:
                     set_dev(prev)
             if rc:
                 _lib.check(rc, "mbx_match_loss")
+        launch.plan_ptr = plan.value
         return launch
 
     def _enqueue_host_step(self):
+        if self.stream is not None:
+            rc = self._staged[0](*self._staged[1])               # H2D copy + kernel on the own stream
+            if rc:
+                _lib.check(rc, "mbx_match_plan_launch_staged")
+            return
         if not self.zero_copy:
             self.d_in.copy_(self.h_in, non_blocking=True)       # one H2D copy of the packed inputs
         self._launch()                                           # one kernel (zero_copy: reads h_in itself)
@@ -597,12 +616,22 @@ class MultiboxLossStep:
             spins += 1
             if spins & 0xffff == 0 and spins > (1 << 22):
                 t0 = time.perf_counter()
-                torch.cuda.current_stream(self.device).synchronize()    # something is wrong: fall back
+                (self.stream or torch.cuda.current_stream(self.device)).synchronize()   # something is wrong: fall back
                 if u[15] == 0:
                     raise RuntimeError("MultiboxLossStep: the kernel finished without publishing its results "
                                        "(%.3f s)" % (time.perf_counter() - t0))
 
     def _ensure_ready(self):
+        if self._launch is None and self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):       # (the workspace is keyed by the stream)
+                self.d_in.copy_(self.h_in, non_blocking=True)
+                self._launch = self.prepare(self.d_loc_in, self.d_conf_in, self.d_gt_in, self.d_ng_in)
+            self.stream.synchronize()
+            lib = _lib.load()
+            self._staged = (lib.mbx_match_plan_launch_staged,
+                            (self._launch.plan_ptr, self.h_in.data_ptr(), self.d_in.data_ptr(),
+                             self.h2d_bytes, self.stream.cuda_stream))
         if self._launch is None:
             host = (self.h_loc, self.h_conf, self.h_gt, self.h_ng) if self.zero_copy else None
             self._launch = self.prepare(self.d_loc_in, self.d_conf_in, self.d_gt_in, self.d_ng_in, inputs=host)
@@ -633,14 +662,16 @@ class MultiboxLossStep:
         if self.peer is None:
             return self.global_losses()
         lib = _lib.load()
-        ws = _workspace(self.device, lib.mbx_match_workspace_bytes(self.B, self.P, self.M))
-        rc = lib.mbx_allreduce_flush(_lib.ptr(self.out["results"]), _lib.ptr(ws), ws.numel(), self.peer.ptr_array,
-                                     self.peer.world, self.peer.rank,
-                                     torch.cuda.current_stream(self.device).cuda_stream)
-        _lib.check(rc, "mbx_allreduce_flush")
-        if self.out["results"] is not self.h_res:
-            self.h_res.copy_(self.out["results"], non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        import contextlib
+        with (torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()):
+            ws = _workspace(self.device, lib.mbx_match_workspace_bytes(self.B, self.P, self.M))
+            rc = lib.mbx_allreduce_flush(_lib.ptr(self.out["results"]), _lib.ptr(ws), ws.numel(), self.peer.ptr_array,
+                                         self.peer.world, self.peer.rank,
+                                         torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(rc, "mbx_allreduce_flush")
+            if self.out["results"] is not self.h_res:
+                self.h_res.copy_(self.out["results"], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
         raise_for_status(self.h_res[2].item())
         return self.global_losses()
 

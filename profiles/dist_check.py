@@ -92,6 +92,34 @@ ok &= okp
 if rank == 0:
     print("dist_check world=%d PDL + deferred, 40 back-to-back steps: fused %.6f %.6f nccl %.6f %.6f -> %s"
           % (world, gl, gc, t64[0].item(), t64[1].item(), "OK" if okp else "MISMATCH"))
+# pipelined host-buffer steps (bench.py's e2e mode): rotating step objects on streams of their own, each with its
+# OWN exchange state; every object's newest step (flush) must equal the NCCL all-reduce of its local sums
+npipe = 4
+objs = [loss.MultiboxLossStep(hi - lo, dp["P"], 20, dp["priors"], dp["alpha"], peer=mdist.PeerAllreduce(),
+                              deferred_allreduce=True, host_results=True, own_stream=True) for _ in range(npipe)]
+pend = []
+for it in range(3 * npipe + 2):
+    o, x = objs[it % npipe], sets[it % 3]
+    if len(pend) == npipe:
+        pend.pop(0).wait()
+    np.copyto(o.h_loc.numpy(), x["locations"])
+    np.copyto(o.h_conf.numpy(), x["confidences"].reshape(hi - lo, -1))
+    np.copyto(o.h_gt.numpy(), x["gt"])
+    np.copyto(o.h_ng.numpy(), x["num_gt"])
+    o.submit_pinned()
+    pend.append(o)
+while pend:
+    pend.pop(0).wait()
+oko = True
+for o in objs:
+    gl, gc = o.flush()
+    t64 = o.h_res[4:8].view(torch.float64).clone().cuda()
+    dist.all_reduce(t64)
+    oko &= abs(gl - t64[0].item()) <= 1e-12 * abs(gl) and abs(gc - t64[1].item()) <= 1e-12 * abs(gc)
+ok &= oko
+if rank == 0:
+    print("dist_check world=%d pipelined own-stream steps (%d objects, one exchange state each): %s -> %s"
+          % (world, npipe, "%.6f %.6f" % (gl, gc), "OK" if oko else "MISMATCH"))
 # the final detection gather: every rank post-processes its shard of one global batch of patches; the packed
 # all-gather must reproduce, bit for bit and in batch order, what one GPU computes on the whole batch
 from multibox_b200 import detect  # noqa: E402

@@ -17,10 +17,11 @@ from multibox_b200 import loss, synth  # noqa: E402
 d = synth.make_train_inputs(**synth.TRAIN_CONFIGS["cfg2"])
 B, P, M = d["B"], d["P"], d["M"]
 K = 2000
-for depth in (1, 2, 3, 4, 5, 7, 9, 11, 15):
+MODES = {"zero_copy+pdl": dict(host_results=True, zero_copy=True, pdl=True),
+         "own_stream": dict(host_results=True, own_stream=True)}     # copy engine + kernel, one stream per object
+for mode, depth in [(m, k) for m in sys.argv[1:] or list(MODES) for k in (1, 2, 3, 4, 5, 7)]:
     n = depth + 1
-    hs = [loss.MultiboxLossStep(B, P, M, d["priors"], d["alpha"], host_results=True, zero_copy=True, pdl=True)
-          for _ in range(n)]
+    hs = [loss.MultiboxLossStep(B, P, M, d["priors"], d["alpha"], **MODES[mode]) for _ in range(n)]
     for r, s_ in enumerate(hs):
         np.copyto(s_.h_loc.numpy(), np.roll(d["locations"], r, 0))
         np.copyto(s_.h_conf.numpy(), np.roll(d["confidences"].reshape(B, P), r, 0))
@@ -42,5 +43,5 @@ for depth in (1, 2, 3, 4, 5, 7, 9, 11, 15):
             pend.pop(0).wait()
         dt = (time.perf_counter() - t0) / K
         best = dt if best is None else min(best, dt)
-    print("depth %2d: %.2f us per step  (%.2f M images/s)" % (depth, 1e6 * best, B / best / 1e6))
+    print("%-14s depth %2d: %.2f us per step  (%.2f M images/s)" % (mode, depth, 1e6 * best, B / best / 1e6))
     del hs

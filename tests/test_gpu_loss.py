@@ -222,6 +222,44 @@ def test_step_object_host_mapped_results(cuda_device, use_graph, zero_copy):
     np.testing.assert_allclose([ll, cl], [ref["location_loss"], ref["confidence_loss"]], rtol=RTOL)
 
 
+def test_step_objects_on_own_streams(cuda_device):
+    """own_stream=True: every object enqueues {H2D copy of its packed pinned inputs, kernel} on a stream of
+    its own with one foreign call (mbx_match_plan_launch_staged); four rotating objects keep several steps
+    in flight (copies and kernels of different steps overlap) and every step returns exactly what the plain
+    path returns for its data, gradients included."""
+    B, n = 32, 4
+    pri = synth.make_train_inputs(K=5, B=1, M=20, seed=0)["priors"]
+    objs = [loss.MultiboxLossStep(B, 646, 20, pri, 1000.0, host_results=True, own_stream=True) for _ in range(n)]
+    plain = loss.MultiboxLossStep(B, 646, 20, pri, 1000.0)
+    data = [synth.make_train_inputs(K=5, B=B, M=20, seed=500 + i) for i in range(7)]
+    want, grads = [], []
+    for d in data:
+        want.append(plain.step_host(d["locations"], d["confidences"], d["gt"], d["num_gt"]))
+        torch.cuda.synchronize()
+        grads.append(plain.out["d_locations"].cpu().clone())
+    pend, got = [], []
+    for rnd in range(3):
+        for i, d in enumerate(data):
+            o = objs[(rnd * len(data) + i) % n]
+            if len(pend) == n:                      # the object is still in flight: complete the oldest step first
+                po, pi = pend.pop(0)
+                got.append((pi, po.wait()))
+                po.stream.synchronize()             # (gradients are read on another stream)
+                assert torch.equal(po.out["d_locations"].cpu(), grads[pi])
+            np.copyto(o.h_loc.numpy(), d["locations"])
+            np.copyto(o.h_conf.numpy(), d["confidences"].reshape(B, -1))
+            np.copyto(o.h_gt.numpy(), d["gt"])
+            np.copyto(o.h_ng.numpy(), d["num_gt"])
+            o.submit_pinned()
+            pend.append((o, i))
+    while pend:
+        po, pi = pend.pop(0)
+        got.append((pi, po.wait()))
+    assert len(got) == 3 * len(data)
+    for pi, val in got:
+        assert val == want[pi]
+    with pytest.raises(ValueError):
+        loss.MultiboxLossStep(B, 646, 20, pri, 1000.0, own_stream=True)      # needs host_results
 
 
 def test_step_pinned_foreign_buffer_all_modes(cuda_device):
