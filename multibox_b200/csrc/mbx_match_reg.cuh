@@ -334,8 +334,10 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     // Launch ticket = step index of this launch in the all-reduce (world > 1): taken by ONE CTA (the collector,
     // else CTA 0) BEFORE it lets the next launch start, so overlapping launches take theirs in stream order.
     unsigned my_step = 0xffffffffu;
-    if (p.ar_world > 1 && static_cast<int>(blockIdx.x) == (has_poster ? n_work : 0)) {
-        __shared__ unsigned sh_step;
+    const bool ticket_cta = p.ar_world > 1 && static_cast<int>(blockIdx.x) == (has_poster ? n_work : 0);
+    const unsigned xp = p.flags >> 28;     // EXPERIMENT selector (profiles/ar_ab.py)
+    __shared__ unsigned sh_step;
+    if (ticket_cta && !(xp & 1u) && !(xp & 8u)) {
         if (tid == 0) sh_step = ar_take_ticket(p);
         block_sync<NWARPS>();
         my_step = sh_step;
@@ -357,6 +359,16 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
             dep_done = true;
         }
     }
+    if (ticket_cta && (xp & 1u) && !(xp & 8u)) {
+        if (tid == 0) sh_step = ar_take_ticket(p);
+        block_sync<NWARPS>();
+        my_step = sh_step;
+    }
+    const unsigned xq = (p.flags >> 24) & 15u;     // EXPERIMENT selector 2
+    if (is_poster && (xp & 2u) && !dep_done) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        dep_done = true;
+    }
     if (is_poster) {
         // The peers' words are self-validating (tag == step + 1) and live in THEIR outboxes, which this launch
         // only reads: nothing here depends on the preceding launch, so the NVLink round trips happen before
@@ -365,13 +377,17 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
         gs.loc = gs.conf = 0.0;
         gs.tag = 0u;
         if (warp == 0) {
-            const unsigned lag = pdl ? 2u : 1u;
+            const unsigned lag = ar_lag(p.flags);
             if (my_step != 0xffffffffu && my_step >= lag && ar_pull_warp(p, my_step - lag, gs.loc, gs.conf))
                 gs.tag = my_step - lag + 1u;
         }
-        if (!dep_done) {
+        if (!dep_done && !(xq & 2u)) {
             asm volatile("griddepcontrol.wait;" ::: "memory");
             dep_done = true;
+        }
+        if (xq & 2u) dep_done = true;   // EXPERIMENT: the collector never waits for the preceding grid (timing only)
+        if (xp & 8u) {   // EXPERIMENT: idle collector (no ticket, no pull), hand-off faked from the step counter
+            gs.tag = __ldcg(p.ar_seq) - ar_lag(p.flags) + 1u;
         }
         if (tid == 0) ar_store_gsum(p, gs);   // (published by this thread's ticket atomic below)
     }
@@ -1114,7 +1130,10 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     block_sync<NWARPS>();
     if (tid == 0) {
         unsigned t;
-        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(p.ticket) : "memory");
+        if (is_poster && (xq & 1u))   // EXPERIMENT: no fence around the collector's ticket (timing only)
+            asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(p.ticket) : "memory");
+        else
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(p.ticket) : "memory");
         is_last = (t == gridDim.x - 1);
     }
     block_sync<NWARPS>();

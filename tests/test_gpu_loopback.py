@@ -66,7 +66,7 @@ def test_deferred_allreduce_loopback(cuda_device, world, mode):
     d, sets = _shards(world, B)
     local = _local_sums(d, sets, world, B)
     peers = mdist.LoopbackPeers(world)
-    lag = 2 if mode == "deferred_pdl" else 1
+    lag = 4 if mode == "deferred_pdl" else 1
     ranks = []
     for r in range(world):
         st = loss.MultiboxLossStep(B, d["P"], d["M"], d["priors"], d["alpha"], peer=peers.rank(r),
@@ -91,8 +91,9 @@ def test_deferred_allreduce_loopback(cuda_device, world, mode):
             loc, glob, gstep, status = _read(ranks[r])
             assert status == 0
             assert np.array_equal(loc, local[s][r])
-            assert gstep == done - lag
-            assert np.array_equal(glob, _expect(local, gstep % NSETS, world)), (mode, world, r, it)
+            assert gstep == max(done - lag, -1)
+            want = _expect(local, gstep % NSETS, world) if gstep >= 0 else np.zeros(2)   # (-1: nothing to complete yet)
+            assert np.array_equal(glob, want), (mode, world, r, it)
         done += 1
     # (b) 40 back-to-back steps without any host synchronisation (overlapping launches under PDL)
     for it in range(40):
