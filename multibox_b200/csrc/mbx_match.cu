@@ -28,6 +28,7 @@
 // Every thread owns the columns j = tid, tid+T, ... so all per-column traffic is
 // conflict-free and needs no barrier; one __syncthreads per Dijkstra step
 // (the block-wide arg-min) and three per augmentation.
+#include <unordered_map>
 #include <new>
 
 #include "mbx_match.cuh"
@@ -206,10 +207,6 @@ __global__ void __launch_bounds__(NWARPS * 32) mbx_match_loss_kernel(const Match
     }
     bool priors_ready = !has_priors;
     int pbuf = 0;
-    // fused all-reduce: every launch takes a ticket (the register-resident family derives the step its
-    // collector CTA pulls from it; this kernel has no collector and completes the reduction in its tail)
-    if (p.ar_world > 1 && blockIdx.x == 0 && tid == 0) (void)ar_take_ticket(p);
-
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         const float4 *gg;
         int n = image_gt(p, b, gg);
@@ -719,7 +716,86 @@ __global__ void mbx_allreduce_flush_kernel(MatchParams p) {   // one warp
         p.results[2] = static_cast<float>(static_cast<unsigned>(p.results[2]) | MBX_STATUS_AR_TIMEOUT);
     }
 }
+
+// The RELAY of the deferred fused all-reduce (see mbx_match.cuh): one warp on a side stream.  Polls this rank's
+// outbox (local memory) for the next step's words and forwards them into every rank's table (lane r: four
+// 8-byte NVLink stores into rank r's buffer; lane == rank: the own table).  Forwards at most `max_steps` steps,
+// exits when no new step appears for `idle_cycles` (the host side launches the next relay kRelaySteps launches
+// later) or the sticky timeout flag is up.  Steps at least kArRing / 2 behind this rank's step counter are
+// skipped: every rank has consumed them (ranks are never more than ar_lag steps apart).
+__global__ void mbx_allreduce_relay_kernel(MatchParams p, int max_steps, long long idle_cycles) {
+    const int lane = threadIdx.x & 31;
+    unsigned char *mine = reinterpret_cast<unsigned char *>(p.ar_peer[p.ar_rank]);
+    volatile unsigned *relayed = reinterpret_cast<volatile unsigned *>(mine + kArRelayedOffset);
+    volatile unsigned *seqp = reinterpret_cast<volatile unsigned *>(p.ar_seq);
+    volatile unsigned *dead = ar_dead_flag(p);
+    unsigned s = *relayed;
+    long long t0 = clock64();
+    for (int n = 0; n < max_steps;) {
+        const unsigned seq = *seqp;
+        if (static_cast<int>(seq - s) >= kArRing / 2) s = seq - kArRing / 2 + 1u;   // (stale: consumed everywhere)
+        const unsigned long long *w = ar_outbox(p.ar_peer[p.ar_rank], s);
+        const unsigned long long w0 = ld_relaxed_sys_u64(w), w1 = ld_relaxed_sys_u64(w + 1),
+                                 w2 = ld_relaxed_sys_u64(w + 2), w3 = ld_relaxed_sys_u64(w + 3);
+        const unsigned tag = s + 1u;
+        if (static_cast<unsigned>(w0 >> 32) == tag && static_cast<unsigned>(w1 >> 32) == tag &&
+            static_cast<unsigned>(w2 >> 32) == tag && static_cast<unsigned>(w3 >> 32) == tag) {
+            if (lane < p.ar_world) {
+                unsigned long long *d = ar_words(p.ar_peer[lane], s, p.ar_rank);
+                st_relaxed_sys_u64(d, w0);
+                st_relaxed_sys_u64(d + 1, w1);
+                st_relaxed_sys_u64(d + 2, w2);
+                st_relaxed_sys_u64(d + 3, w3);
+            }
+            ++s;
+            ++n;
+            if (lane == 0) *relayed = s;
+            t0 = clock64();
+            continue;
+        }
+        if (*dead != 0u || clock64() - t0 > idle_cycles) break;
+    }
+}
 }  // namespace mbx
+
+namespace {
+// Host side of the relay: one side stream per device and a launch counter per symmetric buffer (thread-local,
+// like the scheduler's launch ids).  Every kRelaySteps-th deferred launch on a buffer enqueues a relay for the
+// next kRelaySteps steps BEFORE the step itself; relays of one device run one after the other on the side
+// stream, so a relay that finds its steps already forwarded moves on at once.  Not during stream capture
+// (a captured step has no host side when it is replayed: its reductions take the pull route).
+struct RelayHost {
+    int dev = -1;
+    cudaStream_t side = nullptr;
+    std::unordered_map<unsigned long long, unsigned> launches;
+};
+void maybe_launch_relay(const MatchParams &p, cudaStream_t st) {
+    static thread_local RelayHost host;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != host.dev) {   // (one side stream per device; a process of this framework drives one GPU)
+        host.side = nullptr;
+        host.launches.clear();
+        host.dev = dev;
+    }
+    unsigned &n = host.launches[p.ar_peer[p.ar_rank]];
+    if (n++ % static_cast<unsigned>(kRelaySteps) != 0u) return;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return;
+    }
+    if (!host.side && cudaStreamCreateWithFlags(&host.side, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        host.side = nullptr;
+        return;   // (no relay: the pull route still completes every reduction)
+    }
+    // idle limit: ~30 us at 2 GHz -- a relay outlives the gaps between back-to-back steps of the latency-bound
+    // shapes it exists for, and holds a trailing synchronisation back by no more than that
+    mbx_allreduce_relay_kernel<<<1, 32, 0, host.side>>>(p, kRelaySteps, 60000ll);
+    cudaGetLastError();
+}
+}  // namespace
 
 extern "C" int mbx_allreduce_flush(float *results, void *workspace, size_t workspace_bytes,
                                    const unsigned long long *peer_buffers, int world, int rank, void *stream) {
@@ -957,6 +1033,7 @@ int mbx::match_loss_impl(const mbx_heads *heads, const float *locations, const f
         if (int e = check_cuda(cudaGetLastError(), "launch mbx_scan_num_gt_kernel")) return e;
     }
     if (flags & MBX_FLAG_GENERIC) p.flags &= ~MBX_FLAG_PDL;   // (the generic kernel has no early-start path)
+    if (world > 1 && (flags & MBX_FLAG_AR_DEFERRED)) maybe_launch_relay(p, st);
     if (!(flags & MBX_FLAG_GENERIC)) {
         // register-resident family first; it declines shapes it has no instantiation for
         const int rc = launch_match_reg(p, nwarps, ncols, st);

@@ -326,22 +326,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     for (int c = 0; c < C; ++c)
         if (tid + c * T >= P) invalid_mask |= 1u << c;
 
-    // Deferred fused all-reduce: the launch appends one extra CTA, the COLLECTOR, which pulls the peers' loss
-    // sums of an earlier step over NVLink while the other CTAs solve (mbx_match.cuh).
-    const bool has_poster = p.ar_world > 1 && (p.flags & MBX_FLAG_AR_DEFERRED);
-    const int n_work = has_poster ? static_cast<int>(gridDim.x) - 1 : static_cast<int>(gridDim.x);
-    const bool is_poster = has_poster && static_cast<int>(blockIdx.x) == n_work;
-    // Launch ticket = step index of this launch in the all-reduce (world > 1): taken by ONE CTA (the collector,
-    // else CTA 0) BEFORE it lets the next launch start, so overlapping launches take theirs in stream order.
-    unsigned my_step = 0xffffffffu;
-    const bool ticket_cta = p.ar_world > 1 && static_cast<int>(blockIdx.x) == (has_poster ? n_work : 0);
-    const unsigned xp = p.flags >> 28;     // EXPERIMENT selector (profiles/ar_ab.py)
-    __shared__ unsigned sh_step;
-    if (ticket_cta && !(xp & 1u) && !(xp & 8u)) {
-        if (tid == 0) sh_step = ar_take_ticket(p);
-        block_sync<NWARPS>();
-        my_step = sh_step;
-    }
+    const int n_work = static_cast<int>(gridDim.x);
     // Programmatic dependent launch (MBX_FLAG_PDL; the launcher sets the stream-serialization attribute):
     // this grid may start while the preceding kernel of the stream -- the previous training step -- is
     // still running; the next one may start as soon as every CTA of this grid is running.  The caller
@@ -354,42 +339,10 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     bool dep_done = !pdl;
     if (pdl) {
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        if (logits && p.conf_out && !is_poster) {   // (writes before the epilogue)
+        if (logits && p.conf_out) {   // (writes before the epilogue)
             asm volatile("griddepcontrol.wait;" ::: "memory");
             dep_done = true;
         }
-    }
-    if (ticket_cta && (xp & 1u) && !(xp & 8u)) {
-        if (tid == 0) sh_step = ar_take_ticket(p);
-        block_sync<NWARPS>();
-        my_step = sh_step;
-    }
-    const unsigned xq = (p.flags >> 24) & 15u;     // EXPERIMENT selector 2
-    if (is_poster && (xp & 2u) && !dep_done) {
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        dep_done = true;
-    }
-    if (is_poster) {
-        // The peers' words are self-validating (tag == step + 1) and live in THEIR outboxes, which this launch
-        // only reads: nothing here depends on the preceding launch, so the NVLink round trips happen before
-        // griddepcontrol.wait, while everybody else solves.  Only the hand-off to the last CTA comes after it.
-        Gsum gs;
-        gs.loc = gs.conf = 0.0;
-        gs.tag = 0u;
-        if (warp == 0) {
-            const unsigned lag = ar_lag(p.flags);
-            if (my_step != 0xffffffffu && my_step >= lag && ar_pull_warp(p, my_step - lag, gs.loc, gs.conf))
-                gs.tag = my_step - lag + 1u;
-        }
-        if (!dep_done && !(xq & 2u)) {
-            asm volatile("griddepcontrol.wait;" ::: "memory");
-            dep_done = true;
-        }
-        if (xq & 2u) dep_done = true;   // EXPERIMENT: the collector never waits for the preceding grid (timing only)
-        if (xp & 8u) {   // EXPERIMENT: idle collector (no ticket, no pull), hand-off faked from the step counter
-            gs.tag = __ldcg(p.ar_seq) - ar_lag(p.flags) + 1u;
-        }
-        if (tid == 0) ar_store_gsum(p, gs);   // (published by this thread's ticket atomic below)
     }
 
     // Image scheduling.  Static (image = CTA index, stride = resident CTAs) when every image has
@@ -410,7 +363,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     }
     unsigned ar_seq_hint = 0xffffffffu;
     bool order_seen = !dyn;
-    for (int q = is_poster ? p.B : static_cast<int>(blockIdx.x); q < p.B;) {
+    for (int q = static_cast<int>(blockIdx.x); q < p.B;) {
         int b = q;
         if (dyn && q >= p.order_first) {
             if (!order_seen) {
@@ -1130,10 +1083,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     block_sync<NWARPS>();
     if (tid == 0) {
         unsigned t;
-        if (is_poster && (xq & 1u))   // EXPERIMENT: no fence around the collector's ticket (timing only)
-            asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(p.ticket) : "memory");
-        else
-            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(p.ticket) : "memory");
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(p.ticket) : "memory");
         is_last = (t == gridDim.x - 1);
     }
     block_sync<NWARPS>();
@@ -1142,10 +1092,10 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     const TailPrefetch pre = tail_prefetch(p);
     CollectPrefetch cpf;
     cpf.step = 0xffffffffu;
-    if (warp == 0 && p.ar_world > 1 && !(p.flags & MBX_FLAG_AR_DEFERRED)) {
-        // blocking mode: the collect's words, requested in the same round as the partials
+    if (warp == 0 && p.ar_world > 1) {   // the collect's words (own table), requested in the same round as the partials
         const unsigned sh = __shfl_sync(0xffffffffu, ar_seq_hint, 0);
-        cpf = ar_collect_prefetch(p.ar_peer, p.ar_world, p.ar_rank, sh);
+        const unsigned lag = (p.flags & MBX_FLAG_AR_DEFERRED) ? ar_lag(p.flags) : 0u;
+        cpf = ar_collect_prefetch(p.ar_peer, p.ar_world, p.ar_rank, (sh != 0xffffffffu && sh >= lag) ? sh - lag : 0xffffffffu);
     }
     double a = 0.0, cc = 0.0, md = 0.0;
     for (int b = tid; b < p.B; b += T) {
@@ -1212,7 +1162,6 @@ int launch_one(const MatchParams &p, cudaStream_t st) {
     }
     int units = info.occ;
     if (units > p.B) units = p.B;
-    const bool poster = p.ar_world > 1 && (p.flags & MBX_FLAG_AR_DEFERRED);
     MatchParams pp = p;
     if (p.B > units && !(p.flags & MBX_FLAG_STATIC)) {
         // more images than resident CTAs: heavy-first order (computed by CTA 0 of the kernel) + dynamic
@@ -1227,7 +1176,7 @@ int launch_one(const MatchParams &p, cudaStream_t st) {
         pp.order_first = (p.M >= 128) ? 0 : units;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(units + (poster ? 1 : 0));
+    cfg.gridDim = dim3(units);
     cfg.blockDim = dim3(NWARPS * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
