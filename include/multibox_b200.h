@@ -201,15 +201,21 @@ int mbx_match_loss_heads(const mbx_heads *heads,
  *   peer_buffers [world]  HOST array of device pointers: rank r's symmetric buffer of
  *                         mbx_allreduce_buffer_bytes() bytes (zero-filled once), mapped
  *                         into this process (CUDA IPC / VMM; torch symmetric memory)
- * With MBX_FLAG_AR_DEFERRED the step leaves its sums in its OWN outbox (local stores: no NVLink traffic on
- * the kernel's tail) and completes an EARLIER step's reduction instead -- the previous one, or the one
- * before it under MBX_FLAG_PDL -- whose words one extra CTA of the launch (the collector) pulls from the
- * peers' outboxes over NVLink while the other CTAs solve; results[14] = index of the step the global sums
- * belong to, -1 = none yet.  No rank waits for a slower peer inside the step; mbx_allreduce_flush completes
- * the newest step on demand.
+ * With MBX_FLAG_AR_DEFERRED the matching kernel does no NVLink access at all: the step leaves its sums in its
+ * OWN outbox (local stores) and completes an EARLIER step's reduction instead -- the previous one, or the one
+ * 12 steps back under MBX_FLAG_PDL (mbx_allreduce_config) -- from its own table, into which a one-warp relay
+ * kernel on a side stream (enqueued by this call every 8 steps) forwards every rank's outbox words; words the
+ * relay has not delivered (CUDA graph replays, a relay that exited idle) are pulled from the peers' outboxes
+ * with loads over NVLink instead.  results[14] = index of the step the global sums belong to, -1 = none yet.
+ * No rank waits for a slower peer inside the step; mbx_allreduce_flush completes the newest step on demand.
  * A rank that never arrives trips MBX_STATUS_AR_TIMEOUT (~2 s) instead of hanging; the condition is
  * sticky (later steps report it at once) until the buffers are zero-filled again with no step in flight. */
 size_t mbx_allreduce_buffer_bytes(void);
+/* Process-wide tuning of the deferred mode (call it identically on every rank, with no step in flight, before
+ * the first deferred step on a buffer or after zero-filling the buffers): `pdl_lag` = how many steps back the
+ * reduction completed by a MBX_FLAG_PDL step lies (default 12; without PDL it is always 1), `relay_batch` = how
+ * many steps' sums the relay kernel forwards over NVLink in one burst under PDL (default 8 = a relay's life). */
+int mbx_allreduce_config(int pdl_lag, int relay_batch);
 int mbx_allreduce_flush(float *results, void *workspace, size_t workspace_bytes,
                         const unsigned long long *peer_buffers, int world, int rank, void *stream);
 int mbx_match_loss_allreduce(const float *locations, const float *confidences,

@@ -34,7 +34,7 @@ RESULT_WORDS = 16
 
 EXPORTS = ("mbx_version", "mbx_last_error", "mbx_device_info",
            "mbx_match_workspace_bytes", "mbx_match_loss", "mbx_match_loss_ragged", "mbx_match_loss_heads",
-           "mbx_allreduce_buffer_bytes", "mbx_match_loss_allreduce", "mbx_allreduce_flush",
+           "mbx_allreduce_buffer_bytes", "mbx_allreduce_config", "mbx_match_loss_allreduce", "mbx_allreduce_flush",
            "mbx_match_plan_create", "mbx_match_plan_launch", "mbx_match_plan_launch_staged", "mbx_match_plan_destroy",
            "mbx_detect_workspace_bytes", "mbx_detect", "mbx_detect_heads",
            "mbx_filter_proposals", "mbx_convert_proposals",
@@ -111,6 +111,8 @@ def load():
         _c_void_p, _c_size_t, _c_void_p]                            # workspace, bytes, stream
     lib.mbx_allreduce_buffer_bytes.restype = _c_size_t
     lib.mbx_allreduce_buffer_bytes.argtypes = []
+    lib.mbx_allreduce_config.restype = _c_int
+    lib.mbx_allreduce_config.argtypes = [_c_int, _c_int]
     lib.mbx_match_loss_allreduce.restype = _c_int
     lib.mbx_match_loss_allreduce.argtypes = lib.mbx_match_loss.argtypes[:-1] + [_c_void_p, _c_int, _c_int, _c_void_p]
     lib.mbx_match_plan_create.restype = _c_int

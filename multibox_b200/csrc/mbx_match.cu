@@ -698,6 +698,8 @@ extern "C" int mbx_match_loss_heads(const mbx_heads *heads, const float *gt_bbox
 
 extern "C" size_t mbx_allreduce_buffer_bytes(void) { return align_up(kArBytes, 256); }
 
+extern "C" int mbx_allreduce_config(int pdl_lag, int relay_batch);
+
 namespace mbx {
 __global__ void mbx_allreduce_flush_kernel(MatchParams p) {   // one warp
     const unsigned seq = *p.ar_seq;
@@ -723,7 +725,7 @@ __global__ void mbx_allreduce_flush_kernel(MatchParams p) {   // one warp
 // exits when no new step appears for `idle_cycles` (the host side launches the next relay kRelaySteps launches
 // later) or the sticky timeout flag is up.  Steps at least kArRing / 2 behind this rank's step counter are
 // skipped: every rank has consumed them (ranks are never more than ar_lag steps apart).
-__global__ void mbx_allreduce_relay_kernel(MatchParams p, int max_steps, long long idle_cycles) {
+__global__ void mbx_allreduce_relay_kernel(MatchParams p, int max_steps, long long idle_cycles, int batch) {
     const int lane = threadIdx.x & 31;
     unsigned char *mine = reinterpret_cast<unsigned char *>(p.ar_peer[p.ar_rank]);
     volatile unsigned *relayed = reinterpret_cast<volatile unsigned *>(mine + kArRelayedOffset);
@@ -734,31 +736,46 @@ __global__ void mbx_allreduce_relay_kernel(MatchParams p, int max_steps, long lo
     for (int n = 0; n < max_steps;) {
         const unsigned seq = *seqp;
         if (static_cast<int>(seq - s) >= kArRing / 2) s = seq - kArRing / 2 + 1u;   // (stale: consumed everywhere)
-        const unsigned long long *w = ar_outbox(p.ar_peer[p.ar_rank], s);
-        const unsigned long long w0 = ld_relaxed_sys_u64(w), w1 = ld_relaxed_sys_u64(w + 1),
-                                 w2 = ld_relaxed_sys_u64(w + 2), w3 = ld_relaxed_sys_u64(w + 3);
-        const unsigned tag = s + 1u;
-        if (static_cast<unsigned>(w0 >> 32) == tag && static_cast<unsigned>(w1 >> 32) == tag &&
-            static_cast<unsigned>(w2 >> 32) == tag && static_cast<unsigned>(w3 >> 32) == tag) {
-            if (lane < p.ar_world) {
-                unsigned long long *d = ar_words(p.ar_peer[lane], s, p.ar_rank);
-                st_relaxed_sys_u64(d, w0);
-                st_relaxed_sys_u64(d + 1, w1);
-                st_relaxed_sys_u64(d + 2, w2);
-                st_relaxed_sys_u64(d + 3, w3);
+        // the NEWEST step of the next batch: when its words are there, the older ones of the batch are, too
+        // (a rank completes its steps in order)
+        const unsigned hi = s + static_cast<unsigned>(batch) - 1u;
+        const unsigned long long *wh = ar_outbox(p.ar_peer[p.ar_rank], hi);
+        const unsigned long long h0 = ld_relaxed_sys_u64(wh), h3 = ld_relaxed_sys_u64(wh + 3);
+        const bool idle = clock64() - t0 > idle_cycles;
+        if ((static_cast<unsigned>(h0 >> 32) == hi + 1u && static_cast<unsigned>(h3 >> 32) == hi + 1u) || idle) {
+            // (idle: forward whatever part of the batch exists, then leave)
+            int sent = 0;
+            for (unsigned q = s; q <= hi; ++q) {
+                const unsigned long long *w = ar_outbox(p.ar_peer[p.ar_rank], q);
+                const unsigned long long w0 = ld_relaxed_sys_u64(w), w1 = ld_relaxed_sys_u64(w + 1),
+                                         w2 = ld_relaxed_sys_u64(w + 2), w3 = ld_relaxed_sys_u64(w + 3);
+                const unsigned tag = q + 1u;
+                if (!(static_cast<unsigned>(w0 >> 32) == tag && static_cast<unsigned>(w1 >> 32) == tag &&
+                      static_cast<unsigned>(w2 >> 32) == tag && static_cast<unsigned>(w3 >> 32) == tag))
+                    break;
+                if (lane < p.ar_world) {
+                    unsigned long long *d = ar_words(p.ar_peer[lane], q, p.ar_rank);
+                    st_relaxed_sys_u64(d, w0);
+                    st_relaxed_sys_u64(d + 1, w1);
+                    st_relaxed_sys_u64(d + 2, w2);
+                    st_relaxed_sys_u64(d + 3, w3);
+                }
+                ++sent;
             }
-            ++s;
-            ++n;
-            if (lane == 0) *relayed = s;
+            s += sent;
+            n += sent;
+            if (lane == 0 && sent) *relayed = s;
+            if (idle) break;
             t0 = clock64();
             continue;
         }
-        if (*dead != 0u || clock64() - t0 > idle_cycles) break;
+        if (*dead != 0u) break;
     }
 }
 }  // namespace mbx
 
 namespace {
+int g_pdl_lag = 12, g_relay_batch = kRelaySteps;
 // Host side of the relay: one side stream per device and a launch counter per symmetric buffer (thread-local,
 // like the scheduler's launch ids).  Every kRelaySteps-th deferred launch on a buffer enqueues a relay for the
 // next kRelaySteps steps BEFORE the step itself; relays of one device run one after the other on the side
@@ -792,10 +809,23 @@ void maybe_launch_relay(const MatchParams &p, cudaStream_t st) {
     }
     // idle limit: ~30 us at 2 GHz -- a relay outlives the gaps between back-to-back steps of the latency-bound
     // shapes it exists for, and holds a trailing synchronisation back by no more than that
-    mbx_allreduce_relay_kernel<<<1, 32, 0, host.side>>>(p, kRelaySteps, 60000ll);
+    // (without PDL a step completes the PREVIOUS step's reduction: its sums must be forwarded one by one)
+    mbx_allreduce_relay_kernel<<<1, 32, 0, host.side>>>(p, kRelaySteps, 60000ll,
+                                                       (p.flags & MBX_FLAG_PDL) ? g_relay_batch : 1);
     cudaGetLastError();
 }
 }  // namespace
+
+extern "C" int mbx_allreduce_config(int pdl_lag, int relay_batch) {
+    if (pdl_lag < 1 || relay_batch < 1 || relay_batch > kRelaySteps || 2 * pdl_lag + relay_batch >= kArRing) {
+        set_error("mbx_allreduce_config: need 1 <= relay_batch <= %d and 2 * pdl_lag + relay_batch < %d", kRelaySteps,
+                  kArRing);
+        return MBX_E_ARG;
+    }
+    g_pdl_lag = pdl_lag;
+    g_relay_batch = relay_batch;
+    return 0;
+}
 
 extern "C" int mbx_allreduce_flush(float *results, void *workspace, size_t workspace_bytes,
                                    const unsigned long long *peer_buffers, int world, int rank, void *stream) {
@@ -1023,6 +1053,7 @@ int mbx::match_loss_impl(const mbx_heads *heads, const float *locations, const f
                          : reinterpret_cast<unsigned *>(ws + wl.ar_seq);
     p.ar_world = world;
     p.ar_rank = rank;
+    p.ar_lag_pdl = static_cast<unsigned>(g_pdl_lag);
     for (int r = 0; r < MBX_MAX_PEERS; ++r) p.ar_peer[r] = (world > 1 && r < world) ? peer_buffers[r] : 0ull;
 
     int nwarps = static_cast<int>((flags >> MBX_FLAG_WARPS_SHIFT) & 0xffu);

@@ -1094,7 +1094,7 @@ mbx_match_loss_reg_kernel(const MatchParams p) {
     cpf.step = 0xffffffffu;
     if (warp == 0 && p.ar_world > 1) {   // the collect's words (own table), requested in the same round as the partials
         const unsigned sh = __shfl_sync(0xffffffffu, ar_seq_hint, 0);
-        const unsigned lag = (p.flags & MBX_FLAG_AR_DEFERRED) ? ar_lag(p.flags) : 0u;
+        const unsigned lag = (p.flags & MBX_FLAG_AR_DEFERRED) ? ar_lag(p) : 0u;
         cpf = ar_collect_prefetch(p.ar_peer, p.ar_world, p.ar_rank, (sh != 0xffffffffu && sh >= lag) ? sh - lag : 0xffffffffu);
     }
     double a = 0.0, cc = 0.0, md = 0.0;

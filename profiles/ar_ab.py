@@ -23,10 +23,14 @@ for sd in range(8):
     dp = synth.make_train_inputs(K=5, B=B * world, M=20, seed=1002 + sd)
     lo, hi = mdist.shard_range(B * world)
     sets.append({k: dp[k][lo:hi] for k in ("locations", "confidences", "gt", "num_gt")})
-variants = [("no all-reduce (N=1 kernel)", None, 0), ("deferred (relay + own table)", 0, 0), ("blocking", 0, 1),
-            ("deferred (relay + own table)", 0, 0)]
+from multibox_b200 import _lib  # noqa: E402
+variants = [("no all-reduce (N=1 kernel)", None, 0), ("deferred lag 4, relay batch 1", (4, 1), 0),
+            ("deferred lag 8, relay batch 4", (8, 4), 0), ("deferred lag 12, relay batch 8 (default)", (12, 8), 0),
+            ("blocking", (12, 8), 1)]
 for name, xp, blocking in variants:
     peer = mdist.PeerAllreduce() if xp is not None else None
+    if xp is not None:
+        _lib.check(_lib.load().mbx_allreduce_config(xp[0], xp[1]), "mbx_allreduce_config")
     step = loss.MultiboxLossStep(B, dp["P"], 20, dp["priors"], dp["alpha"], peer=peer, deferred_allreduce=not blocking,
                                  pdl=True)
     launches = [step.prepare(dev_(x["locations"]), dev_(x["confidences"]).view(B, -1), dev_(x["gt"]), dev_(x["num_gt"]))

@@ -66,7 +66,7 @@ def test_deferred_allreduce_loopback(cuda_device, world, mode):
     d, sets = _shards(world, B)
     local = _local_sums(d, sets, world, B)
     peers = mdist.LoopbackPeers(world)
-    lag = 4 if mode == "deferred_pdl" else 1
+    lag = 12 if mode == "deferred_pdl" else 1
     ranks = []
     for r in range(world):
         st = loss.MultiboxLossStep(B, d["P"], d["M"], d["priors"], d["alpha"], peer=peers.rank(r),
@@ -82,7 +82,7 @@ def test_deferred_allreduce_loopback(cuda_device, world, mode):
     torch.cuda.synchronize()
     done = NSETS                      # steps every rank has run so far; step k used set k % NSETS
     # (a) synchronised steps: every result block names its step and carries that step's global sums
-    for it in range(5):
+    for it in range(lag + 4):
         s = done % NSETS
         for r in range(world):
             launches[r][s]()
