@@ -733,12 +733,14 @@ def main():
                        "gradients stay on the device for the backward pass; wall clock.  'one_in_flight_value' = submit, "
                        "poll, next (CUDA graph of one kernel that streams the inputs over PCIe itself; the round-1 mode)"},
         "gpu_launches": tr["launches_per_step"] * args.steps,
-        "collective": ("loss SUM all-reduce fused into the kernel over NVLink peer memory (tagged 8-byte words, no "
-                       "fence / remote atomic): step k leaves its sums in its own outbox and completes step k-2's "
-                       "reduction (k-1's without PDL) from the words one extra CTA pulled from the peers' outboxes "
-                       "while the others solved; the last step is flushed after the timed region; no NCCL call per "
-                       "step; allreduce_check = the fused global sums of the last step against an NCCL all-reduce of "
-                       "the ranks' local fp64 sums") if world > 1 else None,
+        "collective": ("loss SUM all-reduce over NVLink peer memory without an NCCL call per step (tagged 8-byte words, "
+                       "no fence / remote atomic): step k leaves its sums in its own outbox (local stores: the "
+                       "matching kernel does no NVLink access), a one-warp relay kernel on a side stream forwards "
+                       "eight steps' words per burst into every rank's table, and step k completes step k-12's "
+                       "reduction (k-1's without PDL) from its own table -- or pulls the words from the peers' "
+                       "outboxes when the relay has not delivered them; the last step is flushed after the timed "
+                       "region; allreduce_check = the fused global sums of the last step against an NCCL "
+                       "all-reduce of the ranks' local fp64 sums") if world > 1 else None,
         "allreduce_check": tr.get("allreduce_check"),
         "last_losses": {"local": tr.get("last"), "global": tr.get("last_global"), "pipelined_local": tr.get("last_pipe")},
         "roofline": {"bound": "hbm", "kernel": "mbx_match_loss_reg_kernel", "achieved": achieved, "peak": peak,
