@@ -414,6 +414,15 @@ def bench_train(d, steps, warmup, world, barrier, peer, want_e2e=True, pdl=True,
         want = [float(x) for x in local.cpu()]
         ok = all(abs(a - b) <= 1e-12 * max(1.0, abs(b)) for a, b in zip(g, want))
         res["allreduce_check"] = "ok" if ok else "MISMATCH fused=%r nccl=%r" % (list(g), want)
+        try:     # (diagnostics only: the symmetric buffer's step counter and pull-route counter, rank-local)
+            raw = peer._keep[0][16:32].view(torch.int32).cpu().tolist()
+            res["allreduce_stats"] = {"steps_on_this_buffer": raw[0], "forwarded_by_relay": raw[1],
+                                      "completed_by_pull_route": raw[3],
+                                      "note": "deferred steps whose words the relay kernel had not delivered were "
+                                              "pulled from the peers' outboxes over NVLink instead (rank 0's "
+                                              "counters since the buffer was created: prepare + warm-up + timed)"}
+        except Exception:       # noqa: BLE001
+            pass
     if want_e2e:
         # host path.  Four step objects (own pinned staging buffer, own mapped result block, own gradients)
         # rotate, so the H2D source is not one hot buffer; the kernel streams the packed pinned inputs
@@ -742,6 +751,7 @@ def main():
                        "region; allreduce_check = the fused global sums of the last step against an NCCL "
                        "all-reduce of the ranks' local fp64 sums") if world > 1 else None,
         "allreduce_check": tr.get("allreduce_check"),
+        "allreduce_stats": tr.get("allreduce_stats"),
         "last_losses": {"local": tr.get("last"), "global": tr.get("last_global"), "pipelined_local": tr.get("last_pipe")},
         "roofline": {"bound": "hbm", "kernel": "mbx_match_loss_reg_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "peak_kind": "of " + peak_kind,

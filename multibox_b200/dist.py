@@ -126,7 +126,8 @@ class PeerAllreduce:
     process of the NVLink box through torch's symmetric memory (CUDA VMM handles exchanged
     over the process group).  PyTorch only allocates and maps; the exchange itself happens inside
     the kernel: tagged 8-byte words, pushed into the peers' tables (blocking mode) or left in the
-    rank's own outbox and pulled by the peers' collector CTAs over NVLink (deferred mode)."""
+    rank's own outbox, from where a relay kernel on a side stream forwards them into the peers' tables
+    (deferred mode: the matching kernel itself does no NVLink access)."""
 
     def __init__(self, group=None, device=None):
         import ctypes
@@ -174,8 +175,8 @@ class PeerAllreduce:
 class LoopbackPeers:
     """`world` ranks of the fused all-reduce emulated on ONE device: the symmetric buffers are plain device
     allocations of this process and `rank(r)` is the `peer=` object of rank r.  The kernels cannot tell the
-    difference (they only see the pointer table), so the whole exchange protocol -- tickets, outboxes,
-    collector CTA, rings, the timeout flag -- runs on a single-GPU box (tests/test_gpu_loopback.py).
+    difference (they only see the pointer table), so the whole exchange protocol -- outboxes, relay kernel,
+    tables, the pull route, rings, the timeout flag -- runs on a single-GPU box (tests/test_gpu_loopback.py).
     Deferred-mode ranks may share a stream (no rank waits for a same-step peer); blocking-mode ranks
     need one stream each, because a rank's kernel spins until every other rank's kernel has posted."""
 

@@ -1,8 +1,9 @@
 """-m gpu: the fused loss all-reduce (mbx_match_loss_allreduce) with several ranks emulated on ONE GPU.
 
 The multi-GPU tests (tests/test_gpu_dist.py, profiles/dist_check.py) need a box with >= 2 GPUs.  The
-exchange protocol itself -- launch tickets, outboxes pulled by the collector CTA, the two-step lag under
-programmatic dependent launch, the push table of the blocking mode, the rings, the sticky timeout flag --
+exchange protocol itself -- outboxes, the relay kernel that forwards them into every rank's table, the pull
+route when it has not, the lag under programmatic dependent launch, the blocking mode, the rings, the sticky
+timeout flag --
 only sees a table of buffer pointers, so `multibox_b200.dist.LoopbackPeers` runs it unchanged with every
 "rank" on the same device.  Semantics checked: SUM of reference loss.py:100-101 over the ranks, added in
 rank order (bit-exact), for the step the result block names (results[14])."""
@@ -72,7 +73,7 @@ def test_deferred_allreduce_loopback(cuda_device, world, mode):
         st = loss.MultiboxLossStep(B, d["P"], d["M"], d["priors"], d["alpha"], peer=peers.rank(r),
                                    deferred_allreduce=True, pdl=(mode == "deferred_pdl"))
         if mode == "deferred_generic":
-            st.flags |= _lib.FLAG_GENERIC     # the shared-memory kernel: no collector CTA, pulls in its tail
+            st.flags |= _lib.FLAG_GENERIC     # the shared-memory kernel family, same tail
         ranks.append(st)
     # prepare() runs one step per (rank, set): steps 0 .. NSETS-1, all ranks in step order
     launches = [[None] * NSETS for _ in range(world)]
