@@ -59,8 +59,9 @@ extern "C" {
 #define MBX_FLAG_BOUNDARY      2u   /* strict py_func boundary (reference loss.py:81): locations
                                        already have the prior added, confidences already have
                                        +1e-10 added; `priors` is ignored */
-#define MBX_FLAG_AR_DEFERRED   8u   /* mbx_match_loss_allreduce: post this step's sums, complete the
-                                       PREVIOUS step's reduction (no waiting for slower peers) */
+#define MBX_FLAG_AR_DEFERRED   8u   /* mbx_match_loss_allreduce: publish this step's sums, complete an
+                                       EARLIER step's reduction (the previous one; 12 back with MBX_FLAG_PDL):
+                                       no waiting for slower peers, no NVLink access inside the kernel */
 #define MBX_FLAG_STATIC        16u  /* keep the static image -> CTA assignment even when the batch exceeds
                                        the resident CTAs (default then: heavy-first dynamic scheduling) */
 #define MBX_FLAG_HOST_RESULTS  32u  /* `results` is mapped pinned HOST memory that the caller polls: the
